@@ -1,0 +1,236 @@
+// Fused short-sequence attention for sm_100a: softmax(Q K^T * scale) V with all keys of one head
+// resident on chip (S <= 256 tokens, head size 64).  One CTA per (query tile of 128 rows, head, image):
+//
+//   warp 4 (one thread)  TMA-loads Q [128x64], K [SKx64], V [SKx64] (bf16, 128B swizzle) straight out of the
+//                        packed QKV activation matrix, issues S = Q K^T (tcgen05.mma, M=128, N=SK, 4 x K=16)
+//                        into TMEM, later O = P V (A operand = P read from TMEM, B = V as an MN-major smem
+//                        operand, SK/16 MMAs) -- no transposes anywhere, no score tensor in HBM.
+//   warps 0-3            one thread per query row (TMEM lane): row max, exp2, bf16 P written back over the
+//                        consumed S columns (tcgen05.st), row sum; then O * 1/sum -> bf16 context.
+//
+// SK = S rounded up to 16; key columns >= S are masked to probability 0, so the extra K/V rows the TMA box
+// picks up (next image's tokens, or zero fill past the end of the matrix) never contribute.
+// TMEM: 256 columns per CTA (S at [0,SK), P overlaid at [0,SK/2), O overlaid at [128,192)), two CTAs per SM
+// so one CTA's softmax overlaps the other's loads and MMAs.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace evt {
+namespace {
+
+constexpr int kHD = 64;
+constexpr int kQRows = 128;
+constexpr int kAttnThreads = 160;
+constexpr int kTmemCols = 256;
+constexpr int kOCol = 128;
+
+struct AttnParams {
+  __nv_bfloat16* ctx;
+  const float* head_mask;
+  long long ldc;
+  int S, SK, heads;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kv_bytes = p.SK * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kQRows * 128;
+  uint8_t* sV = sK + kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_bytes);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int a = p.heads * kHD;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmKV);
+      ptx::mbar_init(bar_load, 1);
+      ptx::mbar_init(bar_s, 1);
+      ptx::mbar_init(bar_p, 128);
+      ptx::mbar_init(bar_o, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int row0 = b * p.S;
+      ptx::mbar_arrive_expect_tx(bar_load, kQRows * 128 + 2 * kv_bytes);
+      ptx::tma_load_2d(sQ, &tmQ, bar_load, h * kHD, row0 + mt * kQRows);
+      ptx::tma_load_2d(sK, &tmKV, bar_load, a + h * kHD, row0);
+      ptx::tma_load_2d(sV, &tmKV, bar_load, 2 * a + h * kHD, row0);
+      ptx::mbar_wait(bar_load, 0);
+      ptx::tc_fence_after();
+      {  // S = Q K^T
+        const uint32_t idesc = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
+        const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
+        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) ptx::mma_f16_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
+        ptx::mma_commit(bar_s);
+      }
+      ptx::mbar_wait(bar_p, 0);
+      ptx::tc_fence_after();
+      {  // O = P V ; P from TMEM (bf16 pairs, 8 columns per K=16), V MN-major from smem (16 key rows = 2048 B per step)
+        const uint32_t idesc = ptx::make_idesc(kQRows, kHD, 1, 0, 1);
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV));
+        const int nk = p.SK / 16;
+        for (int k = 0; k < nk; ++k)
+          ptx::mma_f16_ts(tmem_base + kOCol, tmem_base + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc,
+                          k != 0 ? 1u : 0u);
+        ptx::mma_commit(bar_o);
+      }
+    }
+  } else {
+    const int qrow = mt * kQRows + warp * 32 + lane;  // query index within the image
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int nchunk = p.SK / 16;
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    // pass 1: row max over the valid keys
+    float m = -CUDART_INF_F;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(t_row + c * 16, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < p.S) m = fmaxf(m, __uint_as_float(r[j]));
+    }
+    // pass 2: probabilities (bf16) written over the S columns already consumed, row sum of the rounded values
+    const float msl = m * p.scale_log2e;
+    float sum = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(t_row + c * 16, r);
+      ptx::tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const int key = c * 16 + j;
+        float p0 = key < p.S ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl)) : 0.f;
+        float p1 = key + 1 < p.S ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl)) : 0.f;
+        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+        const float2 back = __bfloat1622float2(hb);
+        sum += back.x + back.y;
+        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+      }
+      ptx::tmem_st_x8(t_row + c * 8, pk);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(bar_p);
+    // epilogue: O / sum
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    float inv = 1.0f / sum;
+    if (p.head_mask != nullptr) inv *= p.head_mask[h];
+    const bool valid = qrow < p.S;
+    __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.S + qrow) * p.ldc + h * kHD;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      ptx::tmem_ld_x32(t_row + kOCol + half * 32, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+          __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+          __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+          o.x = *reinterpret_cast<uint32_t*>(&t0);
+          o.y = *reinterpret_cast<uint32_t*>(&t1);
+          o.z = *reinterpret_cast<uint32_t*>(&t2);
+          o.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(dst + half * 32 + j) = o;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
+                     int heads, int head_size, float scale, cudaStream_t stream) {
+  EVT_CHECK_ARG(qkv && ctx, "attention: null pointer");
+  EVT_CHECK_ARG(B > 0 && S > 0 && heads > 0, "attention: B, S, heads must be positive");
+  if (head_size != kHD) return fail(EVT_ERR_UNSUPPORTED, "attention: only head size 64 is implemented");
+  if (S > 256) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence length above 256 is not implemented");
+  EVT_CHECK_ARG(ldq >= 3ll * heads * kHD && ldc >= static_cast<int64_t>(heads) * kHD, "attention: leading dimension too small");
+  EVT_CHECK_ARG(ldc % 8 == 0 && reinterpret_cast<uintptr_t>(ctx) % 16 == 0, "attention: ctx must be 16-byte aligned rows");
+  EVT_CHECK_ARG(static_cast<int64_t>(B) * S < (1ll << 31) - 512, "attention: B*S too large");
+  const int SK = (S + 15) / 16 * 16;
+  CUtensorMap tmQ, tmKV;
+  const uint64_t rows = static_cast<uint64_t>(B) * S;
+  int rc = make_tmap_2d(&tmQ, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), kQRows, kHD);
+  if (rc != EVT_OK) return rc;
+  rc = make_tmap_2d(&tmKV, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), SK, kHD);
+  if (rc != EVT_OK) return rc;
+  AttnParams p;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+  p.head_mask = head_mask;
+  p.ldc = ldc;
+  p.S = S;
+  p.SK = SK;
+  p.heads = heads;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  const int smem = 1024 + kQRows * 128 + 2 * SK * 128 + 64;
+  static int configured_dev = -1;
+  int dev = 0;
+  EVT_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + kQRows * 128 + 2 * 256 * 128 + 64));
+    configured_dev = dev;
+  }
+  dim3 grid((S + kQRows - 1) / kQRows, heads, B);
+  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmKV, p);
+  EVT_LAUNCH_CHECK("attention_kernel");
+  return EVT_OK;
+}
+
+}  // namespace evt
+
+extern "C" int evt_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B,
+                                 int S, int heads, int head_size, float scale, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::attention_launch(qkv, ldq, ctx, ldc, head_mask, B, S, heads, head_size, scale,
+                               static_cast<cudaStream_t>(stream));
+}

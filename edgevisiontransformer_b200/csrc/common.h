@@ -1,0 +1,46 @@
+// Host-side plumbing shared by all translation units of libevt: status / error string, launch
+// counting, and TMA tensor-map encoding through the driver entry point (no link-time libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/evt.h"
+
+namespace evt {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void count_launch(int n = 1);
+
+#define EVT_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) return ::evt::fail(EVT_ERR_INVALID, (msg));       \
+  } while (0)
+
+#define EVT_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return ::evt::fail(EVT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+  } while (0)
+
+// After a kernel launch: catch configuration errors without synchronising.
+#define EVT_LAUNCH_CHECK(name)                                                                           \
+  do {                                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                                 \
+    if (_e != cudaSuccess)                                                                               \
+      return ::evt::fail(EVT_ERR_CUDA, std::string("launch ") + (name) + ": " + cudaGetErrorString(_e)); \
+    ::evt::count_launch();                                                                               \
+  } while (0)
+
+int num_sms();
+
+// 2-D row-major tensor map: `rows` x `cols` elements of `elem_bytes`, leading dimension ld (elements),
+// box = box_rows x box_cols, 128-byte swizzle (box_cols * elem_bytes must be 128).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace evt

@@ -1,0 +1,208 @@
+// Memory-bound gather / elementwise kernels around the GEMMs: patch im2col, cls / distillation token
+// rows, fp32 -> bf16 cast, T2T soft-split unfold.  All are coalesced 16- or 32-byte-per-thread streams.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace evt {
+namespace {
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One thread = 8 consecutive pixels of one image row (32 B in, 16 B out).  Thread order follows the
+// input (b, c, y, x8) so reads are perfectly coalesced; writes are full 16-byte pieces of patch rows.
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ cols,
+                                                     int B, int H, int W, int P, long long total) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int w8 = W / 8;
+  const int x8 = static_cast<int>(t % w8);
+  long long r = t / w8;
+  const int y = static_cast<int>(r % H);
+  r /= H;
+  const int c = static_cast<int>(r % 3);
+  const int b = static_cast<int>(r / 3);
+  const float4 v0 = *reinterpret_cast<const float4*>(px + t * 8);
+  const float4 v1 = *reinterpret_cast<const float4*>(px + t * 8 + 4);
+  const int x = x8 * 8;
+  const int py = y / P, i = y % P, pxi = x / P, j = x % P;
+  const int gw = W / P, gh = H / P;
+  const long long row = (static_cast<long long>(b) * gh + py) * gw + pxi;
+  const int k = (c * P + i) * P + j;
+  uint4 o;
+  o.x = pack_bf16(v0.x, v0.y);
+  o.y = pack_bf16(v0.z, v0.w);
+  o.z = pack_bf16(v1.x, v1.y);
+  o.w = pack_bf16(v1.z, v1.w);
+  *reinterpret_cast<uint4*>(cols + row * (3ll * P * P) + k) = o;
+}
+
+// Same gather, f32 output (tf32 mode keeps the patch matrix in fp32).
+__global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict__ px, float* __restrict__ cols, int B,
+                                                         int H, int W, int P, long long total) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int w4 = W / 4;
+  const int x4 = static_cast<int>(t % w4);
+  long long r = t / w4;
+  const int y = static_cast<int>(r % H);
+  r /= H;
+  const int c = static_cast<int>(r % 3);
+  const int b = static_cast<int>(r / 3);
+  const float4 v = *reinterpret_cast<const float4*>(px + t * 4);
+  const int x = x4 * 4;
+  const int py = y / P, i = y % P, pxi = x / P, j = x % P;
+  const int gw = W / P, gh = H / P;
+  const long long row = (static_cast<long long>(b) * gh + py) * gw + pxi;
+  const int k = (c * P + i) * P + j;
+  *reinterpret_cast<float4*>(cols + row * (3ll * P * P) + k) = v;
+}
+
+__global__ void __launch_bounds__(256) prefix_tokens_kernel(const float* __restrict__ prefix,
+                                                            const float* __restrict__ pos, float* __restrict__ out,
+                                                            int B, int tokens, int n_prefix, int D) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * n_prefix * D;
+  if (t >= total) return;
+  const int d = static_cast<int>(t % D);
+  const int tk = static_cast<int>((t / D) % n_prefix);
+  const long long b = t / (static_cast<long long>(D) * n_prefix);
+  out[(b * tokens + tk) * D + d] = prefix[tk * D + d] + pos[tk * D + d];
+}
+
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                   long long n8, long long n) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n8) {
+    const float4 a = *reinterpret_cast<const float4*>(x + t * 8);
+    const float4 b = *reinterpret_cast<const float4*>(x + t * 8 + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(b.x, b.y);
+    o.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(y + t * 8) = o;
+  } else if (t == n8) {
+    for (long long i = n8 * 8; i < n; ++i) y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// tf_Unfold (channel-last): out[(b, oy, ox), (ky, kx, c)] = x[b, oy*s - p + ky, ox*s - p + kx, c], zero outside.
+// One thread per output element pair-of-channels would be wasteful for C = 3, so: one thread per output
+// element, consecutive threads along the output row (kx, c fastest) -> contiguous writes and, within a
+// window row, contiguous reads of kx*C values.
+template <typename TIN>
+__global__ void __launch_bounds__(256) unfold_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                     long long ldo, int B, int H, int W, int C, int k, int s, int p,
+                                                     int oh, int ow, long long total) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int col = static_cast<int>(t % ldo);
+  const long long row = t / ldo;
+  const int kkc = k * k * C;
+  float v = 0.f;
+  if (col < kkc) {
+    const int c = col % C;
+    const int kx = (col / C) % k;
+    const int ky = col / (C * k);
+    const int ox = static_cast<int>(row % ow);
+    const int oy = static_cast<int>((row / ow) % oh);
+    const long long b = row / (static_cast<long long>(ow) * oh);
+    const int iy = oy * s - p + ky, ix = ox * s - p + kx;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = static_cast<float>(x[((b * H + iy) * W + ix) * C + c]);
+  }
+  out[row * ldo + col] = __float2bfloat16_rn(v);
+}
+
+}  // namespace
+
+int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st) {
+  EVT_CHECK_ARG(pixels && cols, "im2col: null pointer");
+  EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && P > 0, "im2col: sizes must be positive");
+  EVT_CHECK_ARG(H % P == 0 && W % P == 0, "im2col: image size must be a multiple of the patch size");
+  EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8");
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(pixels) % 16 == 0 && reinterpret_cast<uintptr_t>(cols) % 16 == 0,
+                "im2col: pointers must be 16-byte aligned");
+  if (out_dtype == EVT_BF16) {
+    const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
+    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        pixels, reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total);
+  } else {
+    const long long total = static_cast<long long>(B) * 3 * H * (W / 4);
+    im2col_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(pixels, reinterpret_cast<float*>(cols),
+                                                                                  B, H, W, P, total);
+  }
+  EVT_LAUNCH_CHECK("im2col");
+  return EVT_OK;
+}
+
+int prefix_tokens_launch(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix, int D,
+                         cudaStream_t st) {
+  EVT_CHECK_ARG(prefix && pos && out, "prefix_tokens: null pointer");
+  EVT_CHECK_ARG(B > 0 && tokens > 0 && n_prefix > 0 && n_prefix <= tokens && D > 0, "prefix_tokens: bad sizes");
+  const long long total = static_cast<long long>(B) * n_prefix * D;
+  prefix_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prefix, pos, out, B, tokens, n_prefix, D);
+  EVT_LAUNCH_CHECK("prefix_tokens");
+  return EVT_OK;
+}
+
+int cast_launch(const float* x, void* y, int64_t n, cudaStream_t st) {
+  EVT_CHECK_ARG(x && y && n > 0, "cast: bad arguments");
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
+                "cast: pointers must be 16-byte aligned");
+  const long long n8 = n / 8;
+  const long long threads = n8 + 1;
+  cast_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n8, n);
+  EVT_LAUNCH_CHECK("cast");
+  return EVT_OK;
+}
+
+int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k, int s, int p,
+                  cudaStream_t st) {
+  EVT_CHECK_ARG(x && out, "unfold: null pointer");
+  EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && s > 0 && p >= 0, "unfold: bad sizes");
+  EVT_CHECK_ARG(ldo >= static_cast<int64_t>(k) * k * C, "unfold: ldo smaller than k*k*C");
+  const int oh = (H + 2 * p - k) / s + 1, ow = (W + 2 * p - k) / s + 1;
+  EVT_CHECK_ARG(oh > 0 && ow > 0, "unfold: empty output");
+  const long long total = static_cast<long long>(B) * oh * ow * ldo;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (x_dtype == EVT_F32)
+    unfold_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(out), ldo,
+                                               B, H, W, C, k, s, p, oh, ow, total);
+  else if (x_dtype == EVT_BF16)
+    unfold_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                       reinterpret_cast<__nv_bfloat16*>(out), ldo, B, H, W, C, k, s, p, oh,
+                                                       ow, total);
+  else
+    return fail(EVT_ERR_INVALID, "unfold: x dtype must be f32 or bf16");
+  EVT_LAUNCH_CHECK("unfold");
+  return EVT_OK;
+}
+
+}  // namespace evt
+
+extern "C" int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::im2col_launch(pixels, cols, EVT_BF16, B, H, W, P, static_cast<cudaStream_t>(stream));
+}
+extern "C" int evt_prefix_tokens(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix,
+                                 int D, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::prefix_tokens_launch(prefix, pos, out, B, tokens, n_prefix, D, static_cast<cudaStream_t>(stream));
+}
+extern "C" int evt_cast_f32_bf16(const float* x, void* y, int64_t n, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::cast_launch(x, y, n, static_cast<cudaStream_t>(stream));
+}
+extern "C" int evt_unfold_nhwc(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k,
+                               int s, int p, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::unfold_launch(x, x_dtype, out, ldo, B, H, W, C, k, s, p, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,390 @@
+// out[M,N] = epilogue(A[M,K] . W[N,K]^T): persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 4      TMA producer   : A tile 128x64 and W tile BNx64 (bf16; 128x32 / BNx32 for tf32) into a
+//                                 STAGES-deep ring of 128B-swizzled shared-memory buffers
+//   warp 5      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16|8) into one of two
+//                                 TMEM accumulator stages (2 x BN columns), commits to mbarriers
+//   warps 0-3   epilogue       : tcgen05.ld the accumulator (lane == row), transpose through a padded
+//                                 per-warp shared tile so that lanes run along N, then bias / GELU /
+//                                 residual and fully coalesced global stores; overlaps the next tile's MMAs
+//
+// Tiles are walked N-fastest so the CTAs resident at one time share a few A row-blocks (read from HBM
+// once) while the whole weight matrix stays in L2.  M, N and K tails are handled by TMA zero fill on the
+// load side and by predication on the store side, so no operand is ever padded in HBM (only leading
+// dimensions must be multiples of 16 bytes).
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace evt {
+namespace {
+
+constexpr int BM = 128;
+constexpr int kStageRowBytes = 128;  // one swizzle row: 64 bf16 or 32 tf32 of K
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 192;
+constexpr int kStgLd = 33;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = BM * kStageRowBytes;
+  static constexpr int kBBytes = BN * kStageRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
+  static constexpr int kTmemCols = BN == 256 ? 512 : BN == 192 ? 512 : BN == 128 ? 256 : 128;
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kStgLd * 4;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kBarBytes;
+};
+
+struct GemmParams {
+  const float* bias;
+  const float* residual;
+  void* out;
+  long long ldr, ldo;
+  int M, N, K;
+  int res_row_mod, res_row_off;
+  int out_group, out_group_stride, out_group_off;
+  int tiles_m, tiles_n, num_kb;
+  int k_step;  // elements of K per stage (64 bf16 / 32 tf32)
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2 + 8 FMA-class ops.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float erfv = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfv);
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) ; u = sqrt(2/pi) (x + 0.044715 x^3)
+  const float u = x * fmaf(0.044715f * 0.7978845608028654f, x * x, 0.7978845608028654f);
+  const float e = exp2f(-2.0f * 1.4426950408889634f * u);
+  return __fdividef(x, 1.0f + e);
+}
+template <int ACT, bool EXACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if (ACT == EVT_ACT_GELU_ERF) {
+    if (EXACT) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    return gelu_erf_fast(v);
+  }
+  if (ACT == EVT_ACT_GELU_TANH) {
+    if (EXACT) return 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
+    return gelu_tanh_fast(v);
+  }
+  return v;
+}
+
+template <int BN, bool TF32, bool OUT_F32, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* staging = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kStagingBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) ptx::tmem_alloc<C::kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          ptx::mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+          ptx::tma_load_2d(sa, &tmA, &full[stage], kb * p.k_step, m0);
+          ptx::tma_load_2d_hint(sb, &tmW, &full[stage], kb * p.k_step, n0, ptx::kEvictLast);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc(BM, BN, TF32 ? 2 : 1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+          const uint64_t adesc = ptx::smem_desc_sw128(sa);
+          const uint64_t bdesc = ptx::smem_desc_sw128(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage row
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            if (TF32) ptx::mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            else ptx::mma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+          }
+          ptx::mma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::mma_commit(&tfull[as]);  // accumulator complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0..3
+    float* stg = staging + warp * 32 * kStgLd;
+    int as = 0;
+    uint32_t aphase = 0;
+    const bool has_res = p.residual != nullptr;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * BM + warp * 32;
+      const int nt0 = (tile % p.tiles_n) * BN;
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + as * BN;
+      const int rows_here = min(32, p.M - m0);  // may be <= 0 for a fully out-of-range warp
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nt0 + c * 32;
+        if (n0 >= p.N) break;
+        uint32_t r[32];
+        ptx::tmem_ld_x32(t_row + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (rows_here > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * kStgLd + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int col = n0 + lane;
+          const bool colok = col < p.N;
+          const float b = (p.bias != nullptr && colok) ? __ldg(p.bias + col) : 0.0f;
+          // incremental row bookkeeping (no per-row division)
+          int grp = 0, pos = 0, rpos = 0;
+          if (p.out_group > 0) {
+            grp = m0 / p.out_group;
+            pos = m0 - grp * p.out_group;
+          }
+          if (p.res_row_mod > 0) rpos = m0 % p.res_row_mod;
+          for (int rr = 0; rr < rows_here; ++rr) {
+            const long long row = m0 + rr;
+            long long orow = row;
+            if (p.out_group > 0) {
+              orow = static_cast<long long>(grp) * p.out_group_stride + p.out_group_off + pos;
+              if (++pos == p.out_group) {
+                pos = 0;
+                ++grp;
+              }
+            }
+            float v = stg[rr * kStgLd + lane] + b;
+            v = apply_act<ACT, TF32>(v);
+            if (colok) {
+              if (has_res) {
+                long long rrow = orow;
+                if (p.res_row_mod > 0) rrow = p.res_row_off + rpos;
+                v += p.residual[rrow * p.ldr + col];
+              }
+              if (OUT_F32) reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = v;
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + col] = __float2bfloat16_rn(v);
+            }
+            if (p.res_row_mod > 0 && ++rpos == p.res_row_mod) rpos = 0;
+          }
+          __syncwarp();
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+int choose_bn(int N) {
+  const int cands[4] = {256, 192, 128, 64};
+  int best = 256;
+  long best_cost = -1;
+  for (int bn : cands) {
+    long cost = static_cast<long>((N + bn - 1) / bn) * bn;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int BN, bool TF32, bool OUT_F32, int ACT>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_kernel<BN, TF32, OUT_F32, ACT>;
+  static bool configured = false;  // per instantiation; attribute is per-device-context but identical everywhere
+  static int configured_dev = -1;
+  int dev = 0;
+  EVT_CUDA(cudaGetDevice(&dev));
+  if (!configured || configured_dev != dev) {
+    EVT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+    configured_dev = dev;
+  }
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, p);
+  EVT_LAUNCH_CHECK("gemm_kernel");
+  return EVT_OK;
+}
+
+template <int BN, bool TF32>
+int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, bool out_f32, int act, cudaStream_t s) {
+  if (out_f32) {
+    switch (act) {
+      case EVT_ACT_NONE: return launch<BN, TF32, true, EVT_ACT_NONE>(a, w, p, s);
+      case EVT_ACT_GELU_ERF: return launch<BN, TF32, true, EVT_ACT_GELU_ERF>(a, w, p, s);
+      default: return launch<BN, TF32, true, EVT_ACT_GELU_TANH>(a, w, p, s);
+    }
+  }
+  switch (act) {
+    case EVT_ACT_NONE: return launch<BN, TF32, false, EVT_ACT_NONE>(a, w, p, s);
+    case EVT_ACT_GELU_ERF: return launch<BN, TF32, false, EVT_ACT_GELU_ERF>(a, w, p, s);
+    default: return launch<BN, TF32, false, EVT_ACT_GELU_TANH>(a, w, p, s);
+  }
+}
+
+}  // namespace
+
+// in_dtype: EVT_BF16 (kind::f16) or EVT_F32 (kind::tf32, operands read as fp32 and truncated to tf32 by the MMA)
+int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias,
+                const float* residual, int64_t ldr, int res_row_mod, int res_row_off, void* out, int out_dtype,
+                int64_t ldo, int out_group, int out_group_stride, int out_group_off, int64_t M, int N, int K, int act,
+                cudaStream_t stream) {
+  EVT_CHECK_ARG(A && W && out, "gemm: null pointer");
+  EVT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive");
+  EVT_CHECK_ARG(M < (1ll << 31) - 256, "gemm: M too large");
+  EVT_CHECK_ARG(in_dtype == EVT_BF16 || in_dtype == EVT_F32, "gemm: input dtype must be bf16 or f32(tf32)");
+  EVT_CHECK_ARG(out_dtype == EVT_BF16 || out_dtype == EVT_F32, "gemm: out dtype must be bf16 or f32");
+  EVT_CHECK_ARG(act >= EVT_ACT_NONE && act <= EVT_ACT_GELU_TANH, "gemm: unknown activation");
+  EVT_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "gemm: leading dimension smaller than the row length");
+  EVT_CHECK_ARG(out_group >= 0 && res_row_mod >= 0, "gemm: negative row-group parameter");
+  EVT_CHECK_ARG(residual == nullptr || ldr >= N, "gemm: residual leading dimension smaller than N");
+  const bool tf32 = in_dtype == EVT_F32;
+  const int eb = tf32 ? 4 : 2;
+  const int k_step = kStageRowBytes / eb;
+  const int bn = choose_bn(N);
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_2d(&tmA, A, eb, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM, k_step);
+  if (rc != EVT_OK) return rc;
+  rc = make_tmap_2d(&tmW, W, eb, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw), bn, k_step);
+  if (rc != EVT_OK) return rc;
+  GemmParams p;
+  p.bias = bias;
+  p.residual = residual;
+  p.out = out;
+  p.ldr = ldr;
+  p.ldo = ldo;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.K = K;
+  p.res_row_mod = res_row_mod;
+  p.res_row_off = res_row_off;
+  p.out_group = out_group;
+  p.out_group_stride = out_group_stride;
+  p.out_group_off = out_group_off;
+  p.tiles_m = static_cast<int>((M + BM - 1) / BM);
+  p.tiles_n = (N + bn - 1) / bn;
+  p.num_kb = (K + k_step - 1) / k_step;
+  p.k_step = k_step;
+  const bool of32 = out_dtype == EVT_F32;
+#define EVT_BN_CASE(BNV)                                                                        \
+  case BNV:                                                                                     \
+    return tf32 ? dispatch_epi<BNV, true>(tmA, tmW, p, of32, act, stream)                       \
+                : dispatch_epi<BNV, false>(tmA, tmW, p, of32, act, stream);
+  switch (bn) {
+    EVT_BN_CASE(256)
+    EVT_BN_CASE(192)
+    EVT_BN_CASE(128)
+    EVT_BN_CASE(64)
+  }
+#undef EVT_BN_CASE
+  return fail(EVT_ERR_INVALID, "gemm: no tile configuration");
+}
+
+}  // namespace evt
+
+extern "C" int evt_gemm_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                 const float* residual, int64_t ldr, int res_row_mod, int res_row_off, void* out,
+                                 int out_dtype, int64_t ldo, int out_group, int out_group_stride, int out_group_off,
+                                 int64_t M, int N, int K, int act, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::gemm_launch(A, lda, W, ldw, EVT_BF16, bias, residual, ldr, res_row_mod, res_row_off, out, out_dtype, ldo,
+                          out_group, out_group_stride, out_group_off, M, N, K, act, static_cast<cudaStream_t>(stream));
+}
+
+// tf32 flavour: A and W are f32 (the MMA reads them as tf32); out is f32.
+extern "C" int evt_gemm_bias_act_tf32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                                      const float* residual, int64_t ldr, int res_row_mod, int res_row_off, float* out,
+                                      int64_t ldo, int out_group, int out_group_stride, int out_group_off, int64_t M,
+                                      int N, int K, int act, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::gemm_launch(A, lda, W, ldw, EVT_F32, bias, residual, ldr, res_row_mod, res_row_off, out, EVT_F32, ldo,
+                          out_group, out_group_stride, out_group_off, M, N, K, act, static_cast<cudaStream_t>(stream));
+}

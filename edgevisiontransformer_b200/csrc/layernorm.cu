@@ -1,0 +1,197 @@
+// LayerNorm kernels (HBM-bound): one warp per row, 8-byte vector loads, the row lives in registers,
+// mean then centred variance (exact for eps = 1e-12 as well as 1e-5), fp32 statistics.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace evt {
+namespace {
+
+constexpr int kMaxVec = 16;  // float2 per lane -> D <= 1024 on the fast path
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// D even, D <= 1024, strides even.  NV = ceil(D / 64).
+template <int NV, bool OUT_BF16>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long x_stride,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      void* __restrict__ y, long long y_stride, float* y_copy,
+                                                      long long rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * x_stride;
+  float2 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 64 + lane * 2;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float2*>(xr + c);
+      s += v[i].x + v[i].y;
+    } else {
+      v[i] = make_float2(0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 64 + lane * 2;
+    if (c < D) {
+      const float a = v[i].x - mean, b = v[i].y - mean;
+      q += a * a + b * b;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 64 + lane * 2;
+    if (c < D) {
+      const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+      const float2 b = *reinterpret_cast<const float2*>(beta + c);
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+      const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      if (OUT_BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(y) + row * y_stride + c) = h;
+      } else {
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(y) + row * y_stride + c) = make_float2(o0, o1);
+      }
+      if (y_copy != nullptr) *reinterpret_cast<float2*>(y_copy + row * x_stride + c) = make_float2(o0, o1);
+    }
+  }
+}
+
+// Any D (odd, > 1024): warp per row, three strided passes over the row (L1/L2 resident).
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, long long x_stride,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, void* __restrict__ y,
+                                                              long long y_stride, float* y_copy, long long rows, int D,
+                                                              float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * x_stride;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float a = xr[c] - mean;
+    q += a * a;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+  for (int c = lane; c < D; c += 32) {
+    const float o = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[row * y_stride + c] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(y)[row * y_stride + c] = o;
+    if (y_copy != nullptr) y_copy[row * x_stride + c] = o;
+  }
+}
+
+// Joint LayerNorm over nh = n*h elements per image (torch_layers dialect): one CTA per image.
+__global__ void __launch_bounds__(1024) ln2d_kernel(const float* __restrict__ x, const float* __restrict__ addend,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float* __restrict__ y, long long nh, float eps) {
+  __shared__ float red[32];
+  __shared__ float stat;
+  const long long base = static_cast<long long>(blockIdx.x) * nh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      float t = lane < nwarp ? red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) stat = t;
+    }
+    __syncthreads();
+    const float r = stat;
+    __syncthreads();
+    return r;
+  };
+  float s = 0.f;
+  for (long long i = tid; i < nh; i += blockDim.x) s += x[base + i] + (addend ? addend[base + i] : 0.f);
+  const float mean = block_sum(s) / static_cast<float>(nh);
+  float q = 0.f;
+  for (long long i = tid; i < nh; i += blockDim.x) {
+    const float a = x[base + i] + (addend ? addend[base + i] : 0.f) - mean;
+    q += a * a;
+  }
+  const float rstd = rsqrtf(block_sum(q) / static_cast<float>(nh) + eps);
+  for (long long i = tid; i < nh; i += blockDim.x) {
+    const float a = x[base + i] + (addend ? addend[base + i] : 0.f);
+    y[base + i] = (a - mean) * rstd * gamma[i] + beta[i];
+  }
+}
+
+template <bool OUT_BF16>
+int launch_rows(const float* x, long long xs, const float* g, const float* b, void* y, long long ys, float* yc,
+                long long rows, int D, float eps, cudaStream_t st) {
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  const bool fast = (D % 2 == 0) && D <= 64 * kMaxVec && (xs % 2 == 0) && (ys % 2 == 0) &&
+                    (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (reinterpret_cast<uintptr_t>(y) % 8 == 0) &&
+                    (reinterpret_cast<uintptr_t>(g) % 8 == 0) && (reinterpret_cast<uintptr_t>(b) % 8 == 0) &&
+                    (yc == nullptr || reinterpret_cast<uintptr_t>(yc) % 8 == 0);
+  if (!fast) {
+    ln_rows_generic_kernel<OUT_BF16><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps);
+  } else {
+    const int nv = (D + 63) / 64;
+#define EVT_LN_CASE(NVV)                                                                          \
+  case NVV:                                                                                       \
+    ln_rows_kernel<NVV, OUT_BF16><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps); \
+    break;
+    switch (nv) {
+      EVT_LN_CASE(1) EVT_LN_CASE(2) EVT_LN_CASE(3) EVT_LN_CASE(4) EVT_LN_CASE(5) EVT_LN_CASE(6) EVT_LN_CASE(7)
+      EVT_LN_CASE(8) EVT_LN_CASE(9) EVT_LN_CASE(10) EVT_LN_CASE(11) EVT_LN_CASE(12) EVT_LN_CASE(13) EVT_LN_CASE(14)
+      EVT_LN_CASE(15) EVT_LN_CASE(16)
+    }
+#undef EVT_LN_CASE
+  }
+  EVT_LAUNCH_CHECK("layernorm");
+  return EVT_OK;
+}
+
+}  // namespace
+
+int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const float* beta, void* y, int y_dtype,
+                     int64_t y_stride, float* y_copy, int64_t rows, int D, float eps, cudaStream_t st) {
+  EVT_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
+  EVT_CHECK_ARG(rows > 0 && D > 0, "layernorm: rows and D must be positive");
+  EVT_CHECK_ARG(x_stride >= D && y_stride >= D, "layernorm: stride smaller than D");
+  EVT_CHECK_ARG(y_dtype == EVT_BF16 || y_dtype == EVT_F32, "layernorm: y dtype must be bf16 or f32");
+  EVT_CHECK_ARG(eps >= 0.f, "layernorm: negative eps");
+  if (y_dtype == EVT_BF16) return launch_rows<true>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
+  return launch_rows<false>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
+}
+
+}  // namespace evt
+
+extern "C" int evt_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta, void* y,
+                                 int y_dtype, int64_t y_stride, float* y_copy_f32, int64_t rows, int D, float eps,
+                                 evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::layernorm_launch(x, x_stride, gamma, beta, y, y_dtype, y_stride, y_copy_f32, rows, D, eps,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int evt_layernorm2d_fwd(const float* x, const float* addend, const float* gamma, const float* beta, float* y,
+                                   int64_t batch, int64_t nh, float eps, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  EVT_CHECK_ARG(x && gamma && beta && y, "layernorm2d: null pointer");
+  EVT_CHECK_ARG(batch > 0 && nh > 0, "layernorm2d: batch and nh must be positive");
+  evt::ln2d_kernel<<<static_cast<unsigned>(batch), 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, addend, gamma, beta,
+                                                                                                 y, nh, eps);
+  EVT_LAUNCH_CHECK("layernorm2d");
+  return EVT_OK;
+}

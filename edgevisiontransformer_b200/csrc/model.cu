@@ -1,0 +1,402 @@
+// Whole-model runtime: owns repacked weights, lays out the caller's workspace, and issues the forward
+// as a fixed sequence of kernel launches on one stream (no allocation, no sync -> CUDA-graph capturable).
+//
+// Forward (HF dialect; SITE/models/vit/modeling_vit.py:620-653, ViTLayer :328-346):
+//   im2col -> patch GEMM (+bias +pos, rows 1.. of each token block) -> cls(+dist) rows
+//   L x [ LN -> QKV GEMM -> attention -> out-proj GEMM (+residual) -> LN -> FC1 GEMM (+GELU) -> FC2 GEMM (+residual) ]
+//   LN on the cls rows only -> classifier GEMM
+// The residual stream is fp32 in HBM; GEMM operands are bf16; LN statistics, softmax and accumulation fp32.
+// TF dialect (modeling/models/vit.py, modeling/layers/norm.py:10-12): LN writes its result back into the
+// residual stream, because there the skip connection carries LN(x).
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ops.h"
+
+namespace evt {
+namespace {
+
+__global__ void __launch_bounds__(256) convert_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          long long rows, int cols, int ld) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= rows * ld) return;
+  const int c = static_cast<int>(t % ld);
+  const long long r = t / ld;
+  dst[t] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+}
+
+// bf16 rows gathered with a stride from an f32 matrix (cls rows for a head without final LN)
+__global__ void __launch_bounds__(256) gather_rows_cast_kernel(const float* __restrict__ x, long long x_stride,
+                                                               __nv_bfloat16* __restrict__ y, long long rows, int D) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= rows * D) return;
+  const int c = static_cast<int>(t % D);
+  const long long r = t / D;
+  y[t] = __float2bfloat16_rn(x[r * x_stride + c]);
+}
+
+inline int pad8(int v) { return (v + 7) / 8 * 8; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct LayerW {
+  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  int a = 0, inter = 0, inter_ld = 0;
+};
+
+}  // namespace
+}  // namespace evt
+
+struct evt_model {
+  evt_model_spec spec;
+  int device = 0;
+  bool loaded = false;
+  int patches = 0, n_prefix = 0, patch_k = 0;
+  std::vector<evt::LayerW> layers;
+  __nv_bfloat16* w_patch = nullptr;
+  float* b_patch = nullptr;
+  float* prefix = nullptr;  // [n_prefix, D]
+  float* pos = nullptr;     // [tokens, D]
+  float *lnf_g = nullptr, *lnf_b = nullptr;
+  __nv_bfloat16* w_pre = nullptr;
+  float* b_pre = nullptr;
+  __nv_bfloat16* w_cls = nullptr;
+  float* b_cls = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace evt {
+namespace {
+
+struct Workspace {
+  float* resid;
+  __nv_bfloat16 *xn, *qkv, *ctx, *big, *clsn, *hh;
+  size_t bytes;
+};
+
+Workspace plan_workspace(const evt_model* m, int batch, void* base) {
+  const evt_model_spec& s = m->spec;
+  const size_t M = static_cast<size_t>(batch) * s.tokens;
+  const size_t Mp = static_cast<size_t>(batch) * m->patches;
+  int amax = 0, imax_ld = 0;
+  for (int l = 0; l < s.layers; ++l) {
+    amax = std::max(amax, s.heads[l] * s.head_size);
+    imax_ld = std::max(imax_ld, pad8(s.inter[l]));
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  Workspace w;
+  const size_t o_resid = take(M * s.hidden * 4);
+  const size_t o_xn = take(M * s.hidden * 2);
+  const size_t o_qkv = take(M * 3 * amax * 2);
+  const size_t o_ctx = take(M * amax * 2);
+  const size_t o_big = take(std::max(M * imax_ld, Mp * static_cast<size_t>(m->patch_k)) * 2);
+  const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * 2);
+  const size_t o_hh = take(static_cast<size_t>(batch) * std::max(pad8(s.head_hidden), 8) * 2);
+  w.resid = reinterpret_cast<float*>(b + o_resid);
+  w.xn = reinterpret_cast<__nv_bfloat16*>(b + o_xn);
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(b + o_qkv);
+  w.ctx = reinterpret_cast<__nv_bfloat16*>(b + o_ctx);
+  w.big = reinterpret_cast<__nv_bfloat16*>(b + o_big);
+  w.clsn = reinterpret_cast<__nv_bfloat16*>(b + o_cls);
+  w.hh = reinterpret_cast<__nv_bfloat16*>(b + o_hh);
+  w.bytes = off;
+  return w;
+}
+
+int validate_spec(const evt_model_spec* s) {
+  EVT_CHECK_ARG(s != nullptr, "model spec is null");
+  EVT_CHECK_ARG(s->dialect == EVT_DIALECT_HF || s->dialect == EVT_DIALECT_TF, "unknown dialect");
+  EVT_CHECK_ARG(s->hidden > 0 && s->hidden % 8 == 0, "hidden size must be a positive multiple of 8");
+  EVT_CHECK_ARG(s->layers > 0 && s->layers <= EVT_MAX_LAYERS, "layer count out of range");
+  EVT_CHECK_ARG(s->patch > 0 && s->image > 0 && s->image % s->patch == 0, "image size must be a multiple of the patch size");
+  EVT_CHECK_ARG(s->patch % 8 == 0, "patch size must be a multiple of 8");
+  const int patches = (s->image / s->patch) * (s->image / s->patch);
+  EVT_CHECK_ARG(s->tokens == patches + 1 || s->tokens == patches + 2, "tokens must be patches + 1 (cls) or + 2 (cls, distillation)");
+  if (s->tokens > 256) return fail(EVT_ERR_UNSUPPORTED, "more than 256 tokens per image is not implemented");
+  if (s->head_size != 64) return fail(EVT_ERR_UNSUPPORTED, "only head size 64 is implemented");
+  EVT_CHECK_ARG(s->num_labels > 0, "num_labels must be positive");
+  EVT_CHECK_ARG(s->act == EVT_ACT_GELU_ERF || s->act == EVT_ACT_GELU_TANH, "FFN activation must be erf- or tanh-GELU");
+  EVT_CHECK_ARG(s->eps > 0.f, "LayerNorm eps must be positive");
+  EVT_CHECK_ARG(s->head_hidden >= 0, "head_hidden must be >= 0");
+  if (s->t2t) return fail(EVT_ERR_UNSUPPORTED, "T2T front-end is driven from the op-level API (evt_unfold_nhwc + performer); model-level t2t is not implemented");
+  for (int l = 0; l < s->layers; ++l) {
+    EVT_CHECK_ARG(s->heads[l] > 0, "every layer must keep at least one head");
+    EVT_CHECK_ARG(s->inter[l] > 0, "every layer must keep at least one FFN unit");
+  }
+  return EVT_OK;
+}
+
+struct Loader {
+  evt_model* m;
+  std::map<std::string, const evt_tensor_view*> by_name;
+  cudaStream_t st;
+
+  const evt_tensor_view* find(const std::string& name) const {
+    auto it = by_name.find(name);
+    return it == by_name.end() ? nullptr : it->second;
+  }
+  static int64_t numel(const evt_tensor_view* v) {
+    int64_t n = 1;
+    for (int i = 0; i < v->ndim; ++i) n *= v->shape[i];
+    return n;
+  }
+  int need(const std::string& name, int64_t n, const evt_tensor_view** out) const {
+    const evt_tensor_view* v = find(name);
+    if (!v) return fail(EVT_ERR_INVALID, "missing weight '" + name + "'");
+    if (!v->data) return fail(EVT_ERR_INVALID, "weight '" + name + "' has a null data pointer");
+    if (numel(v) != n)
+      return fail(EVT_ERR_INVALID, "weight '" + name + "' has " + std::to_string(numel(v)) + " elements, expected " + std::to_string(n));
+    *out = v;
+    return EVT_OK;
+  }
+  int alloc(size_t bytes, void** out) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return fail(EVT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    m->allocs.push_back(p);
+    *out = p;
+    return EVT_OK;
+  }
+  // f32 copy of a vector / table; zero-filled when `optional` and absent
+  int vec(const std::string& name, int64_t n, bool optional, float** out) {
+    void* p;
+    int rc = alloc(n * 4, &p);
+    if (rc) return rc;
+    const evt_tensor_view* v = find(name);
+    if (!v && optional) {
+      EVT_CUDA(cudaMemsetAsync(p, 0, n * 4, st));
+    } else {
+      rc = need(name, n, &v);
+      if (rc) return rc;
+      EVT_CUDA(cudaMemcpyAsync(p, v->data, n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    *out = reinterpret_cast<float*>(p);
+    return EVT_OK;
+  }
+  // bf16 [rows, ld] from f32 [rows, cols] into dst (already allocated), zero padded
+  int mat_into(const std::string& name, int64_t rows, int cols, int ld, __nv_bfloat16* dst) {
+    const evt_tensor_view* v;
+    int rc = need(name, rows * cols, &v);
+    if (rc) return rc;
+    const long long total = rows * ld;
+    convert_pad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float*>(v->data), dst, rows, cols, ld);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EVT_ERR_CUDA, std::string("convert_pad: ") + cudaGetErrorString(e));
+    return EVT_OK;
+  }
+  int mat(const std::string& name, int64_t rows, int cols, int ld, __nv_bfloat16** out) {
+    void* p;
+    int rc = alloc(static_cast<size_t>(rows) * ld * 2, &p);
+    if (rc) return rc;
+    *out = reinterpret_cast<__nv_bfloat16*>(p);
+    return mat_into(name, rows, cols, ld, *out);
+  }
+};
+
+}  // namespace
+}  // namespace evt
+
+using namespace evt;
+
+extern "C" int evt_model_create(const evt_model_spec* spec, evt_model** out) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  EVT_CHECK_ARG(out != nullptr, "evt_model_create: out is null");
+  rc = validate_spec(spec);
+  if (rc != EVT_OK) return rc;
+  evt_model* m = new evt_model();
+  m->spec = *spec;
+  cudaGetDevice(&m->device);
+  m->patches = (spec->image / spec->patch) * (spec->image / spec->patch);
+  m->n_prefix = spec->tokens - m->patches;
+  m->patch_k = 3 * spec->patch * spec->patch;
+  m->layers.resize(spec->layers);
+  *out = m;
+  return EVT_OK;
+}
+
+extern "C" int evt_model_destroy(evt_model* m) {
+  if (!m) return EVT_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return EVT_OK;
+}
+
+extern "C" int evt_model_load_weights(evt_model* m, const evt_tensor_view* tensors, int n, evt_stream stream) {
+  EVT_CHECK_ARG(m != nullptr && tensors != nullptr && n > 0, "evt_model_load_weights: bad arguments");
+  if (m->loaded) return fail(EVT_ERR_STATE, "weights already loaded; create a new model to reload");
+  const evt_model_spec& s = m->spec;
+  Loader L;
+  L.m = m;
+  L.st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n; ++i) {
+    EVT_CHECK_ARG(tensors[i].name != nullptr, "tensor view without a name");
+    EVT_CHECK_ARG(tensors[i].ndim >= 1 && tensors[i].ndim <= 4, "tensor view rank must be 1..4");
+    L.by_name[tensors[i].name] = &tensors[i];
+  }
+  const int D = s.hidden;
+  int rc;
+#define EVT_TRY(expr) \
+  do {                \
+    rc = (expr);      \
+    if (rc != EVT_OK) return rc; \
+  } while (0)
+  const std::string e = "vit.embeddings.";
+  EVT_TRY(L.mat(e + "patch_embeddings.projection.weight", D, m->patch_k, m->patch_k, &m->w_patch));
+  EVT_TRY(L.vec(e + "patch_embeddings.projection.bias", D, false, &m->b_patch));
+  EVT_TRY(L.vec(e + "position_embeddings", static_cast<int64_t>(s.tokens) * D, false, &m->pos));
+  {
+    void* p;
+    EVT_TRY(L.alloc(static_cast<size_t>(m->n_prefix) * D * 4, &p));
+    m->prefix = reinterpret_cast<float*>(p);
+    const evt_tensor_view* v;
+    EVT_TRY(L.need(e + "cls_token", D, &v));
+    EVT_CUDA(cudaMemcpyAsync(m->prefix, v->data, D * 4, cudaMemcpyDeviceToDevice, L.st));
+    if (m->n_prefix == 2) {
+      EVT_TRY(L.need(e + "distillation_token", D, &v));
+      EVT_CUDA(cudaMemcpyAsync(m->prefix + D, v->data, D * 4, cudaMemcpyDeviceToDevice, L.st));
+    }
+  }
+  for (int l = 0; l < s.layers; ++l) {
+    LayerW& w = m->layers[l];
+    const std::string p = "vit.encoder.layer." + std::to_string(l) + ".";
+    w.a = s.heads[l] * s.head_size;
+    w.inter = s.inter[l];
+    w.inter_ld = pad8(w.inter);
+    void* q;
+    EVT_TRY(L.alloc(static_cast<size_t>(3) * w.a * D * 2, &q));
+    w.wqkv = reinterpret_cast<__nv_bfloat16*>(q);
+    EVT_TRY(L.alloc(static_cast<size_t>(3) * w.a * 4, &q));
+    w.bqkv = reinterpret_cast<float*>(q);
+    const char* names[3] = {"query", "key", "value"};
+    for (int t = 0; t < 3; ++t) {
+      const std::string base = p + "attention.attention." + names[t];
+      EVT_TRY(L.mat_into(base + ".weight", w.a, D, D, w.wqkv + static_cast<size_t>(t) * w.a * D));
+      const evt_tensor_view* v = L.find(base + ".bias");
+      if (v) {
+        EVT_TRY(L.need(base + ".bias", w.a, &v));
+        EVT_CUDA(cudaMemcpyAsync(w.bqkv + t * w.a, v->data, w.a * 4, cudaMemcpyDeviceToDevice, L.st));
+      } else {
+        EVT_CUDA(cudaMemsetAsync(w.bqkv + t * w.a, 0, w.a * 4, L.st));
+      }
+    }
+    EVT_TRY(L.mat(p + "attention.output.dense.weight", D, w.a, w.a, &w.wo));
+    EVT_TRY(L.vec(p + "attention.output.dense.bias", D, true, &w.bo));
+    EVT_TRY(L.mat(p + "intermediate.dense.weight", w.inter, D, D, &w.w1));
+    EVT_TRY(L.vec(p + "intermediate.dense.bias", w.inter, true, &w.b1));
+    EVT_TRY(L.mat(p + "output.dense.weight", D, w.inter, w.inter_ld, &w.w2));
+    EVT_TRY(L.vec(p + "output.dense.bias", D, true, &w.b2));
+    EVT_TRY(L.vec(p + "layernorm_before.weight", D, false, &w.ln1_g));
+    EVT_TRY(L.vec(p + "layernorm_before.bias", D, false, &w.ln1_b));
+    EVT_TRY(L.vec(p + "layernorm_after.weight", D, false, &w.ln2_g));
+    EVT_TRY(L.vec(p + "layernorm_after.bias", D, false, &w.ln2_b));
+  }
+  if (s.final_ln) {
+    EVT_TRY(L.vec("vit.layernorm.weight", D, false, &m->lnf_g));
+    EVT_TRY(L.vec("vit.layernorm.bias", D, false, &m->lnf_b));
+  }
+  int cls_in = D;
+  if (s.head_hidden > 0) {
+    EVT_TRY(L.mat("pre_classifier.weight", s.head_hidden, D, D, &m->w_pre));
+    EVT_TRY(L.vec("pre_classifier.bias", s.head_hidden, true, &m->b_pre));
+    cls_in = s.head_hidden;
+  }
+  EVT_TRY(L.mat("classifier.weight", s.num_labels, cls_in, pad8(cls_in), &m->w_cls));
+  EVT_TRY(L.vec("classifier.bias", s.num_labels, true, &m->b_cls));
+#undef EVT_TRY
+  EVT_CUDA(cudaStreamSynchronize(L.st));
+  m->loaded = true;
+  return EVT_OK;
+}
+
+extern "C" int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* out) {
+  EVT_CHECK_ARG(m != nullptr && out != nullptr, "evt_model_workspace_bytes: null argument");
+  EVT_CHECK_ARG(batch > 0, "batch must be positive");
+  *out = plan_workspace(m, batch, nullptr).bytes + 1024;  // slack to align the caller's pointer
+  return EVT_OK;
+}
+
+extern "C" int evt_model_launches_per_forward(const evt_model* m) {
+  if (!m) return 0;
+  const evt_model_spec& s = m->spec;
+  return 3 + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+}
+
+extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits, void* workspace,
+                                 size_t workspace_bytes, evt_stream stream) {
+  EVT_CHECK_ARG(m != nullptr, "evt_model_forward: model is null");
+  if (!m->loaded) return fail(EVT_ERR_STATE, "evt_model_forward called before evt_model_load_weights");
+  EVT_CHECK_ARG(pixels && logits && workspace, "evt_model_forward: null pointer");
+  EVT_CHECK_ARG(batch > 0 && batch <= 65535, "batch must be in 1..65535");
+  const evt_model_spec& s = m->spec;
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const size_t slack = reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(workspace);
+  Workspace w = plan_workspace(m, batch, base);
+  EVT_CHECK_ARG(w.bytes + slack <= workspace_bytes, "workspace too small for this batch (see evt_model_workspace_bytes)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = s.hidden;
+  const int64_t M = static_cast<int64_t>(batch) * s.tokens;
+  const int64_t Mp = static_cast<int64_t>(batch) * m->patches;
+  const bool tf = s.dialect == EVT_DIALECT_TF;
+  const float scale = 1.0f / sqrtf(static_cast<float>(s.head_size));
+  int rc;
+#define EVT_TRY(expr) \
+  do {                \
+    rc = (expr);      \
+    if (rc != EVT_OK) return rc; \
+  } while (0)
+  // embeddings
+  EVT_TRY(im2col_launch(pixels, w.big, EVT_BF16, batch, s.image, s.image, s.patch, st));
+  EVT_TRY(gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, EVT_BF16, m->b_patch, m->pos, D, m->patches, m->n_prefix,
+                      w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
+  EVT_TRY(prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
+  // encoder
+  for (int l = 0; l < s.layers; ++l) {
+    const LayerW& lw = m->layers[l];
+    const int a = lw.a;
+    EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, EVT_BF16, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    EVT_TRY(gemm_launch(w.xn, D, lw.wqkv, D, EVT_BF16, lw.bqkv, nullptr, 0, 0, 0, w.qkv, EVT_BF16, 3 * a, 0, 0, 0, M, 3 * a,
+                        D, EVT_ACT_NONE, st));
+    EVT_TRY(attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
+    EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, EVT_BF16, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
+                        EVT_ACT_NONE, st));
+    EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, EVT_BF16, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    EVT_TRY(gemm_launch(w.xn, D, lw.w1, D, EVT_BF16, lw.b1, nullptr, 0, 0, 0, w.big, EVT_BF16, lw.inter_ld, 0, 0, 0, M,
+                        lw.inter, D, s.act, st));
+    EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, EVT_BF16, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0,
+                        0, M, D, lw.inter, EVT_ACT_NONE, st));
+  }
+  // head: only the cls row of every image is consumed (SITE/models/vit/modeling_vit.py:641)
+  const int64_t tok_stride = static_cast<int64_t>(s.tokens) * D;
+  if (s.final_ln) {
+    EVT_TRY(layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, EVT_BF16, D, nullptr, batch, D, s.eps, st));
+  } else {
+    const long long total = static_cast<long long>(batch) * D;
+    gather_rows_cast_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w.resid, tok_stride, w.clsn, batch, D);
+    EVT_LAUNCH_CHECK("gather_rows_cast");
+  }
+  if (s.head_hidden > 0) {
+    const int hl = pad8(s.head_hidden);
+    EVT_TRY(gemm_launch(w.clsn, D, m->w_pre, D, EVT_BF16, m->b_pre, nullptr, 0, 0, 0, w.hh, EVT_BF16, hl, 0, 0, 0, batch,
+                        s.head_hidden, D, EVT_ACT_GELU_TANH, st));
+    EVT_TRY(gemm_launch(w.hh, hl, m->w_cls, hl, EVT_BF16, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0,
+                        batch, s.num_labels, s.head_hidden, EVT_ACT_NONE, st));
+  } else {
+    EVT_TRY(gemm_launch(w.clsn, D, m->w_cls, D, EVT_BF16, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0,
+                        batch, s.num_labels, D, EVT_ACT_NONE, st));
+  }
+#undef EVT_TRY
+  return EVT_OK;
+}

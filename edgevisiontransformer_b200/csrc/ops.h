@@ -1,0 +1,25 @@
+// Internal launchers shared between the op-level C ABI and the model runtime.
+#pragma once
+#include "common.h"
+
+namespace evt {
+
+int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias,
+                const float* residual, int64_t ldr, int res_row_mod, int res_row_off, void* out, int out_dtype,
+                int64_t ldo, int out_group, int out_group_stride, int out_group_off, int64_t M, int N, int K, int act,
+                cudaStream_t stream);
+
+int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
+                     int heads, int head_size, float scale, cudaStream_t stream);
+
+int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const float* beta, void* y, int y_dtype,
+                     int64_t y_stride, float* y_copy, int64_t rows, int D, float eps, cudaStream_t st);
+
+int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st);
+int prefix_tokens_launch(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix, int D,
+                         cudaStream_t st);
+int cast_launch(const float* x, void* y, int64_t n, cudaStream_t st);
+int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k, int s, int p,
+                  cudaStream_t st);
+
+}  // namespace evt

@@ -1,0 +1,301 @@
+"""Drop-in B200 ViT / DeiT image classifier.
+
+Replaces, for inference, the module the reference evaluates and prunes:
+``model(images).logits`` of HF ``ViTForImageClassification`` (deit_pruning/src/utils.py:194-195,
+are_16_heads/classifier_eval.py:69-70).  Construct it FROM the (already pruned / optimised) HF module
+with :meth:`from_hf`, from an HF-named state dict with :meth:`from_state_dict`, or from a checkpoint
+directory with :meth:`from_pretrained` (edgevisiontransformer_b200.checkpoint).  Per-layer head counts and FFN widths
+are read off the weight shapes, so nn_pruning / are16heads models with uneven layers load as they are.
+
+The forward runs entirely inside libevt (hand-written sm_100a kernels); torch only owns the tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+@dataclass
+class B200ViTConfig:
+    hidden_size: int = 192
+    num_hidden_layers: int = 12
+    heads: List[int] = field(default_factory=lambda: [3] * 12)          # surviving heads per layer
+    intermediate: List[int] = field(default_factory=lambda: [768] * 12)  # FFN width per layer
+    head_size: int = 64
+    tokens: int = 197
+    image_size: int = 224
+    patch_size: int = 16
+    num_labels: int = 1000
+    layer_norm_eps: float = 1e-12
+    hidden_act: str = "gelu"          # "gelu" (erf) | "gelu_new"/"gelu_tanh" (tanh)
+    dialect: str = "hf"               # "hf" | "tf"
+    final_ln: bool = True
+    head_hidden: int = 0
+
+    # names the reference's callers read off model.config
+    @property
+    def num_attention_heads(self):
+        return max(self.heads)
+
+    @property
+    def intermediate_size(self):
+        return max(self.intermediate)
+
+
+@dataclass
+class ImageClassifierOutput:
+    logits: torch.Tensor
+    loss: Optional[torch.Tensor] = None
+
+    def __getitem__(self, i):
+        return (self.logits,)[i]
+
+
+_ACT = {"gelu": _lib.ACT_GELU_ERF, "gelu_erf": _lib.ACT_GELU_ERF, "gelu_new": _lib.ACT_GELU_TANH,
+        "gelu_tanh": _lib.ACT_GELU_TANH, "gelu_pytorch_tanh": _lib.ACT_GELU_TANH, "tanh": _lib.ACT_GELU_TANH}
+
+
+def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12, hidden_act="gelu", head_size=64,
+                           image_size=224, patch_size=16, dialect="hf", final_ln=None, head_hidden=None) -> B200ViTConfig:
+    D = sd["vit.embeddings.cls_token"].shape[-1]
+    L = 0
+    while f"vit.encoder.layer.{L}.attention.attention.query.weight" in sd:
+        L += 1
+    if L == 0:
+        raise ValueError("state dict has no vit.encoder.layer.0.attention.attention.query.weight")
+    heads, inter = [], []
+    for l in range(L):
+        a = sd[f"vit.encoder.layer.{l}.attention.attention.query.weight"].shape[0]
+        if a % head_size:
+            raise ValueError(f"layer {l}: query rows {a} not a multiple of the head size {head_size}")
+        heads.append(a // head_size)
+        inter.append(sd[f"vit.encoder.layer.{l}.intermediate.dense.weight"].shape[0])
+    if final_ln is None:
+        final_ln = "vit.layernorm.weight" in sd
+    if head_hidden is None:
+        head_hidden = sd["pre_classifier.weight"].shape[0] if "pre_classifier.weight" in sd else 0
+    return B200ViTConfig(hidden_size=D, num_hidden_layers=L, heads=heads, intermediate=inter, head_size=head_size,
+                         tokens=sd["vit.embeddings.position_embeddings"].shape[-2], image_size=image_size,
+                         patch_size=patch_size, num_labels=sd["classifier.weight"].shape[0],
+                         layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, dialect=dialect, final_ln=bool(final_ln),
+                         head_hidden=int(head_hidden))
+
+
+class B200ViTForImageClassification(nn.Module):
+    """Inference-only; weights are repacked (bf16, padded) inside libevt at construction."""
+
+    def __init__(self, config: B200ViTConfig, state_dict: Dict[str, torch.Tensor], device=None, max_batch: int = 1024,
+                 keep_params: bool = True):
+        super().__init__()
+        device = torch.device(device if device is not None else "cuda")
+        if device.type != "cuda":
+            raise RuntimeError("B200ViTForImageClassification runs only on a CUDA (sm_100a) device; no CPU fallback")
+        self.config = config
+        self.max_batch = int(max_batch)
+        self._device = device
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_batch = 0
+        self._graphs: Dict[int, tuple] = {}
+        spec = _lib.ModelSpec()
+        spec.dialect = _lib.DIALECT_TF if config.dialect == "tf" else _lib.DIALECT_HF
+        spec.hidden, spec.layers, spec.tokens = config.hidden_size, config.num_hidden_layers, config.tokens
+        spec.image, spec.patch, spec.head_size = config.image_size, config.patch_size, config.head_size
+        spec.num_labels = config.num_labels
+        if config.hidden_act not in _ACT:
+            raise ValueError(f"unsupported hidden_act {config.hidden_act!r}")
+        spec.act = _ACT[config.hidden_act]
+        spec.eps = float(config.layer_norm_eps)
+        if config.num_hidden_layers > _lib.MAX_LAYERS:
+            raise ValueError("too many layers")
+        for l in range(config.num_hidden_layers):
+            spec.heads[l] = int(config.heads[l])
+            spec.inter[l] = int(config.intermediate[l])
+        spec.final_ln = int(config.final_ln)
+        spec.head_hidden = int(config.head_hidden)
+        spec.t2t = 0
+        with torch.cuda.device(device):
+            _lib.check(self._lib.evt_model_create(C.byref(spec), C.byref(self._handle)), "model_create")
+            dev_sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in state_dict.items()
+                      if torch.is_tensor(v) and v.is_floating_point()}
+            views = (_lib.TensorView * len(dev_sd))()
+            keep = []
+            for i, (k, v) in enumerate(dev_sd.items()):
+                name = k.encode()
+                keep.append(name)
+                views[i].name = name
+                views[i].data = v.data_ptr()
+                views[i].ndim = max(1, min(v.dim(), 4))
+                shp = list(v.shape)[-4:] if v.dim() > 4 else list(v.shape)
+                if v.dim() > 4:   # collapse leading dims
+                    shp[0] = v.numel() // (shp[1] * shp[2] * shp[3])
+                for j, s in enumerate(shp or [1]):
+                    views[i].shape[j] = s
+            _lib.check(self._lib.evt_model_load_weights(self._handle, views, len(dev_sd),
+                                                        torch.cuda.current_stream().cuda_stream), "model_load_weights")
+        if keep_params:
+            self._names = list(dev_sd.keys())
+            self._params = nn.ParameterList([nn.Parameter(v, requires_grad=False) for v in dev_sd.values()])
+        else:
+            self._names = ["classifier.bias"]
+            self._params = nn.ParameterList([nn.Parameter(dev_sd["classifier.bias"], requires_grad=False)])
+        self.eval()
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], config: Optional[B200ViTConfig] = None, **kw):
+        sd = normalise_keys(sd)
+        cfg_kw = {k: kw.pop(k) for k in list(kw) if k in ("layer_norm_eps", "hidden_act", "head_size", "image_size",
+                                                            "patch_size", "dialect", "final_ln", "head_hidden")}
+        config = config or config_from_state_dict(sd, **cfg_kw)
+        return cls(config, sd, **kw)
+
+    @classmethod
+    def from_hf(cls, model: nn.Module, **kw):
+        """Build from a live HF ViT/DeiT classifier AFTER any surgery (prune_heads, optimize_model):
+        shapes come from the module tree (deit_pruning/src/eval_main.py:87-103 order of operations)."""
+        hf_cfg = model.config
+        sd = normalise_keys({k: v for k, v in model.state_dict().items()})
+        config = config_from_state_dict(
+            sd, layer_norm_eps=getattr(hf_cfg, "layer_norm_eps", 1e-12), hidden_act=getattr(hf_cfg, "hidden_act", "gelu"),
+            head_size=hf_cfg.hidden_size // hf_cfg.num_attention_heads, image_size=_first(hf_cfg.image_size),
+            patch_size=_first(hf_cfg.patch_size))
+        return cls(config, sd, **kw)
+
+    @classmethod
+    def from_pretrained(cls, model_dir: str, **kw):
+        from .checkpoint import load_checkpoint
+        sd, cfg_kw = load_checkpoint(model_dir)
+        cfg_kw.update({k: kw.pop(k) for k in list(kw) if k in ("hidden_act", "layer_norm_eps")})
+        return cls.from_state_dict(sd, **cfg_kw, **kw)
+
+    # ------------------------------------------------------------------ nn.Module surface
+    def num_parameters(self, only_trainable: bool = False) -> int:
+        return 0 if only_trainable else sum(p.numel() for p in self._params)
+
+    def state_dict(self, *a, **kw):  # HF-named view of the weights this model was built from
+        return {n: p.detach() for n, p in zip(self._names, self._params)}
+
+    def to(self, *args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, (str, torch.device)):
+                dev = torch.device(a)
+        dev = torch.device(kwargs["device"]) if "device" in kwargs else dev
+        if dev is not None and (dev.type != "cuda" or (dev.index is not None and dev.index != self._device.index
+                                                       and self._device.index is not None)):
+            raise RuntimeError("B200ViTForImageClassification is bound to its CUDA device; rebuild it to move it")
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda" if device is None else device))
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise RuntimeError("B200ViTForImageClassification is inference-only")
+        return super().train(False)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.evt_model_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, batch: int) -> torch.Tensor:
+        if self._ws is None or batch > self._ws_batch:
+            n = C.c_size_t()
+            _lib.check(self._lib.evt_model_workspace_bytes(self._handle, batch, C.byref(n)), "workspace_bytes")
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=self._device)
+            self._ws_batch = batch
+            self._graphs.clear()
+        return self._ws
+
+    def _run(self, pixels: torch.Tensor, logits: torch.Tensor) -> None:
+        B = pixels.shape[0]
+        ws = self._workspace(B)
+        _lib.check(self._lib.evt_model_forward(self._handle, pixels.data_ptr(), B, logits.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), torch.cuda.current_stream().cuda_stream), "model_forward")
+
+    @torch.no_grad()
+    def forward(self, pixel_values: Optional[torch.Tensor] = None, labels=None, **ignored) -> ImageClassifierOutput:
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        x = pixel_values
+        if not x.is_cuda:
+            raise RuntimeError("pixel_values must be a CUDA tensor (no CPU fallback); move the batch with .to(device)")
+        c = self.config
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != c.image_size or x.shape[3] != c.image_size:
+            raise ValueError(f"Input image size ({tuple(x.shape[2:])}) doesn't match model ({c.image_size}*{c.image_size}).")
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B = x.shape[0]
+        logits = torch.empty((B, c.num_labels), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self._device):
+            for s in range(0, B, self.max_batch):
+                e = min(B, s + self.max_batch)
+                self._run(x[s:e], logits[s:e])
+        return ImageClassifierOutput(logits=logits)
+
+    # ------------------------------------------------------------------ latency path: CUDA graph
+    @torch.no_grad()
+    def forward_graphed(self, pixel_values: torch.Tensor) -> ImageClassifierOutput:
+        """Same result as forward(); the launch sequence for this batch size is captured once in a CUDA graph
+        and replayed, removing per-kernel launch overhead at small batch."""
+        B = pixel_values.shape[0]
+        if B > self.max_batch:
+            return self.forward(pixel_values)
+        ent = self._graphs.get(B)
+        with torch.cuda.device(self._device):
+            if ent is None:
+                self._workspace(B)
+                static_in = torch.empty((B, 3, self.config.image_size, self.config.image_size), dtype=torch.float32,
+                                        device=self._device)
+                static_out = torch.empty((B, self.config.num_labels), dtype=torch.float32, device=self._device)
+                static_in.copy_(pixel_values)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        self._run(static_in, static_out)
+                torch.cuda.current_stream().wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(static_in, static_out)
+                ent = (g, static_in, static_out)
+                self._graphs[B] = ent
+            g, static_in, static_out = ent
+            static_in.copy_(pixel_values)
+            g.replay()
+            return ImageClassifierOutput(logits=static_out.clone())
+
+    def launches_per_forward(self) -> int:
+        return int(self._lib.evt_model_launches_per_forward(self._handle))
+
+
+def _first(v):
+    return v[0] if isinstance(v, (tuple, list)) else v
+
+
+def normalise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Accept HF ViT ('vit.'), HF DeiT ('deit.') and DDP ('module.') prefixes; 'cls_classifier' -> 'classifier'."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("module."):
+            k = k[len("module."):]
+        if k.startswith("deit."):
+            k = "vit." + k[len("deit."):]
+        if k.startswith("cls_classifier."):
+            k = "classifier." + k[len("cls_classifier."):]
+        out[k] = v
+    return out

@@ -1,0 +1,182 @@
+"""Op-level torch wrappers over the libevt C ABI.  torch supplies device memory and the stream only.
+
+Every function requires CUDA tensors; a CPU tensor raises (there is no CPU path in the product).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EVT_BF16, EVT_F32  # noqa: F401
+
+ACTS = {None: ACT_NONE, "none": ACT_NONE, "gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF, "erf": ACT_GELU_ERF,
+        "gelu_tanh": ACT_GELU_TANH, "tanh": ACT_GELU_TANH, "gelu_new": ACT_GELU_TANH}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("edgevisiontransformer_b200 ops need CUDA tensors on a B200 (sm_100a); "
+                               "there is no CPU fallback")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return EVT_F32
+    if t.dtype == torch.bfloat16:
+        return EVT_BF16
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out_dtype: torch.dtype = torch.bfloat16, write_back: bool = False) -> torch.Tensor:
+    """LayerNorm over the last dim of an f32 tensor whose rows are contiguous. write_back: x <- LN(x) too."""
+    _need_cuda(x, gamma, beta)
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise ValueError("layernorm wants an f32 tensor with unit inner stride")
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    if x2.data_ptr() != x.data_ptr():
+        raise ValueError("layernorm wants a tensor viewable as [rows, D]")
+    y = torch.empty(x2.shape, dtype=out_dtype, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_layernorm_fwd(x2.data_ptr(), x2.stride(0), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _dt(y),
+                                     y.stride(0), x2.data_ptr() if write_back else None, x2.shape[0], D, float(eps),
+                                     _stream()), "layernorm")
+    return y.view(*x.shape)
+
+
+def layernorm_rows(x: torch.Tensor, row_stride: int, rows: int, D: int, gamma, beta, eps, out_dtype=torch.bfloat16):
+    """LayerNorm of `rows` rows of length D spaced row_stride elements apart (cls rows of [B,S,D])."""
+    _need_cuda(x, gamma, beta)
+    y = torch.empty((rows, D), dtype=out_dtype, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_layernorm_fwd(x.data_ptr(), row_stride, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _dt(y), D,
+                                     None, rows, D, float(eps), _stream()), "layernorm")
+    return y
+
+
+def layernorm2d(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Joint LayerNorm over the last two dims of f32 x[B,n,h] (+addend), affine [n,h]."""
+    _need_cuda(x, gamma, beta, addend)
+    x = x.contiguous()
+    if addend is not None:
+        addend = addend.contiguous()
+    B = x.shape[0]
+    nh = x[0].numel()
+    if gamma.numel() != nh or beta.numel() != nh:
+        raise ValueError("layernorm2d: affine parameters must have n*h elements")
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    _lib.check(lib.evt_layernorm2d_fwd(x.data_ptr(), _ptr(addend), gamma.contiguous().data_ptr(),
+                                       beta.contiguous().data_ptr(), y.data_ptr(), B, nh, float(eps), _stream()),
+               "layernorm2d")
+    return y
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act=None,
+           residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+           out: Optional[torch.Tensor] = None, n: Optional[int] = None, k: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16 (tensor cores, f32 accumulate) or
+    both f32 (tf32 mode).  Row strides may exceed the logical K / N (padded leading dimensions)."""
+    _need_cuda(a, w, bias, residual, out)
+    if a.dim() != 2 or w.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("linear wants 2-D operands with unit inner stride")
+    if a.dtype != w.dtype:
+        raise ValueError("linear: a and w must have the same dtype")
+    M = a.shape[0]
+    K = k if k is not None else a.shape[1]
+    N = n if n is not None else w.shape[0]
+    if w.shape[1] < K or a.shape[1] < K:
+        raise ValueError("linear: K exceeds operand width")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if residual is not None and (residual.dtype != torch.float32 or residual.stride(1) != 1):
+        raise ValueError("linear: residual must be f32 with unit inner stride")
+    lib = _lib.load()
+    act_id = ACTS[act] if not isinstance(act, int) else act
+    if a.dtype == torch.bfloat16:
+        rc = lib.evt_gemm_bias_act(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual),
+                                   residual.stride(0) if residual is not None else 0, 0, 0, out.data_ptr(), _dt(out),
+                                   out.stride(0), 0, 0, 0, M, N, K, act_id, _stream())
+    elif a.dtype == torch.float32:
+        if out.dtype != torch.float32:
+            raise ValueError("linear: tf32 mode writes f32")
+        rc = lib.evt_gemm_bias_act_tf32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(residual),
+                                        residual.stride(0) if residual is not None else 0, 0, 0, out.data_ptr(),
+                                        out.stride(0), 0, 0, 0, M, N, K, act_id, _stream())
+    else:
+        raise ValueError(f"linear: unsupported dtype {a.dtype}")
+    _lib.check(rc, "gemm")
+    return out
+
+
+def attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_size: int = 64, scale: Optional[float] = None,
+              head_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv bf16 [B*S, 3*heads*head_size] (q | k | v blocks) -> ctx bf16 [B*S, heads*head_size]."""
+    _need_cuda(qkv, head_mask)
+    if qkv.dtype != torch.bfloat16 or qkv.dim() != 2 or qkv.stride(1) != 1:
+        raise ValueError("attention wants a 2-D bf16 qkv matrix")
+    if qkv.shape[0] != B * S or qkv.shape[1] < 3 * heads * head_size:
+        raise ValueError("attention: qkv shape does not match B, S, heads")
+    ctx = torch.empty((B * S, heads * head_size), dtype=torch.bfloat16, device=qkv.device)
+    scale = float(head_size ** -0.5 if scale is None else scale)
+    lib = _lib.load()
+    _lib.check(lib.evt_attention_fwd(qkv.data_ptr(), qkv.stride(0), ctx.data_ptr(), ctx.stride(0), _ptr(head_mask), B, S,
+                                     heads, head_size, scale, _stream()), "attention")
+    return ctx
+
+
+def im2col_patch(pixels: torch.Tensor, patch: int = 16) -> torch.Tensor:
+    _need_cuda(pixels)
+    if pixels.dtype != torch.float32 or pixels.dim() != 4 or pixels.shape[1] != 3:
+        raise ValueError("im2col_patch wants f32 NCHW pixels with 3 channels")
+    pixels = pixels.contiguous()
+    B, _, H, W = pixels.shape
+    cols = torch.empty((B * (H // patch) * (W // patch), 3 * patch * patch), dtype=torch.bfloat16, device=pixels.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_im2col_patch(pixels.data_ptr(), cols.data_ptr(), B, H, W, patch, _stream()), "im2col")
+    return cols
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        raise ValueError("cast_bf16 wants f32")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast")
+    return y
+
+
+def unfold_nhwc(x: torch.Tensor, k: int, s: int, p: int, ld: Optional[int] = None) -> torch.Tensor:
+    """tf_Unfold (channel-last): x [B,H,W,C] f32|bf16 -> bf16 [B*oh*ow, ld] (ld >= k*k*C, zero padded)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, H, W, Cc = x.shape
+    oh, ow = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    ld = ld or (k * k * Cc + 7) // 8 * 8
+    out = torch.empty((B * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_unfold_nhwc(x.data_ptr(), _dt(x), out.data_ptr(), ld, B, H, W, Cc, k, s, p, _stream()), "unfold")
+    return out
+
+
+def launch_count(reset: bool = False) -> int:
+    lib = _lib.load()
+    n = int(lib.evt_launch_count())
+    if reset:
+        lib.evt_launch_count_reset()
+    return n

@@ -1,0 +1,178 @@
+/*
+ * libevt -- B200-native (sm_100a) ViT / DeiT / T2T inference forward behind a C ABI.
+ *
+ * The reference (xudoong/EdgeVisionTransformer) has no FFI for this path: callers invoke a
+ * Python nn.Module (`model(images).logits`, deit_pruning/src/utils.py:194-195,
+ * are_16_heads/classifier_eval.py:69-70; op-level models utils.py:322-365).  This header is the
+ * boundary a binding for that path would use; INTEGRATION.md shows the ctypes stub.  Each entry
+ * point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = EVT_OK, negative = EVT_ERR_*; never throws.
+ *   - evt_last_error() returns a thread-local message for the last failing call.
+ *   - all data pointers are DEVICE pointers unless the name says host; `stream` is a cudaStream_t.
+ *   - calls are asynchronous on `stream`: no allocation, no host sync, CUDA-graph capturable,
+ *     unless stated otherwise.
+ *   - there is no CPU fallback: a device that is not compute capability 10.x -> EVT_ERR_UNSUPPORTED.
+ *   - bf16 matrices given to the GEMM / attention ops need 16-byte aligned base pointers and
+ *     leading dimensions that are multiples of 8 elements (TMA requirement).
+ */
+#ifndef EVT_H_
+#define EVT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVT_VERSION 100
+
+enum evt_status {
+  EVT_OK = 0,
+  EVT_ERR_INVALID = -1,      /* bad argument (maps to ValueError in the Python wrapper)   */
+  EVT_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed                        */
+  EVT_ERR_UNSUPPORTED = -3,  /* not an sm_100 device, or shape outside the kernel's range  */
+  EVT_ERR_STATE = -4         /* call order violated (e.g. forward before weights loaded)   */
+};
+
+enum evt_dtype { EVT_F32 = 0, EVT_BF16 = 1 };
+
+/* activation fused in the GEMM epilogue.  ERF: HF `hidden_act="gelu"`
+ * (SITE/models/vit/modeling_vit.py:291-299); TANH: modeling/torch_layers/activation.py:4-7. */
+enum evt_act { EVT_ACT_NONE = 0, EVT_ACT_GELU_ERF = 1, EVT_ACT_GELU_TANH = 2 };
+
+typedef void* evt_stream;
+
+const char* evt_last_error(void);
+int evt_version(void);
+/* EVT_OK when the current CUDA device can run the kernels (compute capability 10.x). */
+int evt_device_check(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+int64_t evt_launch_count(void);
+void evt_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ op level ------------- */
+
+/* LayerNorm over the last dim of `rows` rows of length D (nn.LayerNorm,
+ * SITE/models/vit/modeling_vit.py:325-326,333,340,455; modeling/layers/norm.py:6).
+ * x: f32, row stride x_stride elements.  y: bf16 or f32 (y_dtype), row stride y_stride.
+ * y_copy_f32 (nullable): also write the normalised row as f32 with stride x_stride -- may alias x
+ * (TF dialect: the skip connection carries LN(x), modeling/layers/norm.py:10-12 + residual.py:8). */
+int evt_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta,
+                      void* y, int y_dtype, int64_t y_stride, float* y_copy_f32,
+                      int64_t rows, int D, float eps, evt_stream stream);
+
+/* Joint LayerNorm over the last TWO dims [n,h] of x[B,n,h] (+ optional addend of the same shape
+ * before normalising), affine gamma/beta [n,h]: modeling/torch_layers/norm.py:4-15 as built at
+ * utils.py:338,364.  All f32. */
+int evt_layernorm2d_fwd(const float* x, const float* addend, const float* gamma, const float* beta,
+                        float* y, int64_t batch, int64_t nh, float eps, evt_stream stream);
+
+/* out[M,N] = epilogue( A[M,K] . W[N,K]^T )   -- nn.Linear (modeling/torch_layers/attention.py:19-22,
+ * ffn.py:10-11; SITE/models/vit/modeling_vit.py:216-218,262,290,305,640-642).
+ *   A, W : bf16 row-major, leading dims lda / ldw (multiples of 8)
+ *   bias : f32 [N] or NULL
+ *   act  : evt_act, applied after bias
+ *   residual : f32 or NULL; added after the activation.  Row r of the output reads residual row
+ *              (res_row_mod > 0 ? res_row_off + r % res_row_mod : out_row(r)), leading dim ldr.
+ *   out  : bf16 or f32 (out_dtype), leading dim ldo.  out_row(r) = r when out_group == 0, else
+ *          (r / out_group) * out_group_stride + out_group_off + r % out_group   (patch-embed rows
+ *          1..196 of each image's 197-token block, SITE/models/vit/modeling_vit.py:117-126).
+ *   residual may alias out (in-place residual stream update). */
+int evt_gemm_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                      const float* residual, int64_t ldr, int res_row_mod, int res_row_off,
+                      void* out, int out_dtype, int64_t ldo,
+                      int out_group, int out_group_stride, int out_group_off,
+                      int64_t M, int N, int K, int act, evt_stream stream);
+
+/* tf32 flavour of evt_gemm_bias_act: A and W are f32 (read as tf32 by the tensor core, f32 accumulate),
+ * out is f32; leading dims multiples of 4.  Used by the tf32 accuracy mode (max-abs 1e-3 on logits). */
+int evt_gemm_bias_act_tf32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                           const float* residual, int64_t ldr, int res_row_mod, int res_row_off,
+                           float* out, int64_t ldo, int out_group, int out_group_stride, int out_group_off,
+                           int64_t M, int N, int K, int act, evt_stream stream);
+
+/* Fused softmax(Q K^T * scale) V for short sequences (S <= 256, head size 64):
+ * eager_attention_forward SITE/models/vit/modeling_vit.py:171-196 ==
+ * modeling/torch_layers/attention.py:36-45 == modeling/layers/attention.py:30-33.
+ *   qkv : bf16 [B*S, ldq]; q of head h at columns [h*64, h*64+64), k at [heads*64 + h*64, ...),
+ *         v at [2*heads*64 + h*64, ...)
+ *   ctx : bf16 [B*S, ldc]; head h written to columns [h*64, h*64+64)
+ *   head_mask : f32 [heads] or NULL; ctx of head h is multiplied by head_mask[h]
+ *               (are_16_heads `mask_heads`, are_16_heads/run_classifier.py:247-250). */
+int evt_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask,
+                      int B, int S, int heads, int head_size, float scale, evt_stream stream);
+
+/* Non-overlapping patch gather: pixels f32 NCHW [B,3,H,W] -> bf16 [B*(H/P)*(W/P), 3*P*P] with
+ * K order (c, i, j) -- the im2col of Conv2d(3,D,P,P) (SITE/models/vit/modeling_vit.py:151-167). */
+int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream);
+
+/* Rows [0, n_prefix) of each image's token block: out[b, t, :] = prefix[t, :] + pos[t, :]
+ * (cls / distillation token + position embedding, SITE/models/vit/modeling_vit.py:117-126). */
+int evt_prefix_tokens(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix,
+                      int D, evt_stream stream);
+
+/* f32 -> bf16 cast of n elements (n multiple of 1; pointers 16-byte aligned). */
+int evt_cast_f32_bf16(const float* x, void* y, int64_t n, evt_stream stream);
+
+/* T2T soft split (tf_Unfold, modeling/models/t2t_vit.py:20-40): x NHWC [B,H,W,C] (f32 or bf16) ->
+ * bf16 [B*oh*ow, ldo] with depth order (kh, kw, c), zero padding p; ldo >= k*k*C, pad cols zeroed. */
+int evt_unfold_nhwc(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C,
+                    int k, int s, int p, evt_stream stream);
+
+/* ------------------------------------------------------------------ model level ---------- */
+
+typedef struct evt_model evt_model;
+
+#define EVT_MAX_LAYERS 64
+
+enum evt_dialect {
+  EVT_DIALECT_HF = 0,   /* HF ViT/DeiT: pre-LN, qkv bias, final LN + Linear head            */
+  EVT_DIALECT_TF = 1    /* modeling/models/vit.py: skip carries LN(x), no qkv bias, no final
+                           LN, 2-layer MLP head; also the T2T-ViT encoder (final LN + Dense) */
+};
+
+typedef struct evt_model_spec {
+  int dialect;                 /* evt_dialect */
+  int hidden;                  /* D */
+  int layers;                  /* L <= EVT_MAX_LAYERS */
+  int tokens;                  /* 197 (cls + 196) or 198 (DeiT distillation token) */
+  int image, patch;            /* 224, 16 */
+  int head_size;               /* 64 */
+  int num_labels;              /* 1000 */
+  int act;                     /* evt_act for the FFN */
+  float eps;                   /* LayerNorm epsilon */
+  int heads[EVT_MAX_LAYERS];   /* surviving heads per layer (HF prune_heads semantics)       */
+  int inter[EVT_MAX_LAYERS];   /* FFN width per layer (optimize_model semantics), any int>0  */
+  int final_ln;                /* 1: LayerNorm before the head (HF, T2T); 0: TF-dialect DeiT */
+  int head_hidden;             /* 0: single Linear head; >0: Dense(head_hidden, gelu)->Dense */
+  int t2t;                     /* 1: T2T front-end (NHWC input) instead of the patch embed   */
+} evt_model_spec;
+
+typedef struct evt_tensor_view {
+  const char* name;            /* weight name, see INTEGRATION.md (HF state_dict keys)        */
+  const void* data;            /* f32, contiguous, DEVICE pointer                              */
+  int ndim;
+  int64_t shape[4];
+} evt_tensor_view;
+
+/* Validate the spec and allocate an empty model on the current device (allocates; not async). */
+int evt_model_create(const evt_model_spec* spec, evt_model** out);
+/* Repack weights into the library's own padded bf16 / f32 buffers (allocates; synchronises `stream`).
+ * The caller keeps ownership of the views.  Missing or mis-shaped tensors -> EVT_ERR_INVALID. */
+int evt_model_load_weights(evt_model* m, const evt_tensor_view* tensors, int n, evt_stream stream);
+/* Bytes of caller-provided scratch needed for a forward at `batch`. */
+int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* out);
+/* logits[batch, num_labels] (f32) = forward(pixels f32 NCHW [batch,3,image,image]); async on stream. */
+int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits,
+                      void* workspace, size_t workspace_bytes, evt_stream stream);
+/* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
+int evt_model_launches_per_forward(const evt_model* m);
+int evt_model_destroy(evt_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVT_H_ */

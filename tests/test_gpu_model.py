@@ -1,0 +1,117 @@
+"""GPU parity of the whole forward (through the C ABI model entry points) against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): bf16 mode -> logits max-abs <= 2e-2 and 100 % top-1 agreement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ViTSpec  # noqa: E402
+from oracle import pruning as opr  # noqa: E402
+from oracle import tf_vit as otf  # noqa: E402
+from oracle import vit as ovit  # noqa: E402
+
+BF16_TOL = 2e-2
+
+
+def _model(sd, **kw):
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    return B200ViTForImageClassification.from_state_dict(sd, **kw)
+
+
+def _check(got, want, tol=BF16_TOL):
+    r = ovit.compare_logits(got, want)
+    assert r["max_abs"] <= tol, r
+    assert r["top1_agree"] == 1.0, r
+    return r
+
+
+@pytest.mark.parametrize("kind,seed,stress,bs", [("tiny", 0, False, 2), ("tiny", 3, True, 5), ("small", 0, True, 3)])
+def test_deit_matches_oracle_and_golden(kind, seed, stress, bs, golden_dir):
+    spec = ViTSpec.deit(kind)
+    hf = ovit.build_hf_model(spec, seed=seed, stress=stress)
+    sd = ovit.state_dict_of(hf)
+    x = ovit.synthetic_images(bs, seed=1)
+    want = ovit.vit_forward(sd, spec, x)
+    m = _model(sd)
+    got = m(x.cuda()).logits
+    _check(got, want)
+    name = {("tiny", 0): "hf_tiny_s0.npz", ("tiny", 3): "hf_tiny_s3_stress.npz", ("small", 0): "hf_small_s0_stress.npz"}[(kind, seed)]
+    f = np.load(os.path.join(golden_dir, name))
+    nb = int(f["batch"])
+    _check(got[:nb], torch.from_numpy(f["logits"]))       # committed fixture from the HF forward itself
+
+
+def test_from_hf_and_module_surface():
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    spec = ViTSpec.deit("tiny")
+    hf = ovit.build_hf_model(spec, seed=2, stress=True)
+    m = B200ViTForImageClassification.from_hf(hf)
+    x = ovit.synthetic_images(3, seed=5)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    out = m(pixel_values=x.cuda())                  # kw call as deit_pruning/src/trainer.py:58
+    _check(out.logits, want)
+    assert next(m.parameters()).device.type == "cuda"        # deit_pruning/src/utils.py:177
+    assert m.num_parameters() == sum(p.numel() for p in hf.parameters())
+    assert m.eval() is m and m.to("cuda") is m
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 192, 192, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m(x)                                        # CPU input: no fallback
+    g = m.forward_graphed(x.cuda()).logits
+    assert torch.equal(g, out.logits)               # graph replay == eager launch sequence, bit for bit
+    assert m.launches_per_forward() == 3 + 7 * 12 + 2
+
+
+@pytest.mark.parametrize("case", ["h1_d230", "head18_uneven"])
+def test_pruned_models(case, golden_dir):
+    spec = ViTSpec.deit("tiny")
+    hf = ovit.build_hf_model(spec, seed=4, stress=True)
+    sd = ovit.state_dict_of(hf)
+    f = np.load(os.path.join(golden_dir, f"pruned_tiny_{case}.npz"))
+    heads_kept = [[0]] * 12 if case == "h1_d230" else opr.kept_heads_from_pruned_str(opr.DEIT_TINY_HEAD18, 12, 3)
+    full, pruned, _ = opr.synthesize_pruned(sd, heads_kept, [int(v) for v in f["inter_kept"]], seed=7)
+    m = _model(pruned)
+    assert m.config.heads == [len(h) for h in heads_kept]
+    assert m.config.intermediate == [int(v) for v in f["inter_kept"]]
+    x = ovit.synthetic_images(2, seed=1)
+    got = m(x.cuda()).logits
+    _check(got, torch.from_numpy(f["logits_opt"]))      # fixture from vendored optimize_model + prune_heads
+    # the full-size checkpoint with zero rows/cols gives the same function
+    got_full = _model(full)(x.cuda()).logits
+    _check(got_full, torch.from_numpy(f["logits_full"]))
+
+
+def test_tf_dialect_matches_restatement():
+    from edgevisiontransformer_b200.dialects import tf_vit_to_canonical
+    sd, heads, inter = otf.init_tf_vit(dim=192, depth=12, seed=1, stress=True)
+    x = ovit.synthetic_images(3, seed=2)
+    want = otf.tf_vit_forward(sd, x, heads)
+    csd, kw = tf_vit_to_canonical(sd, heads)
+    got = _model(csd, **kw)(x.cuda()).logits
+    _check(got, want, tol=3e-2)
+    # ViT_Pruned 'layerwise' encoding (modeling/models/vit.py:58-97)
+    h2, i2 = opr.parse_prune_encoding("layerwise_" + "_".join(["h2-d0.5", "h1-d0.3", "h3-d1.0"] * 4), 12, 768)
+    sd, heads, inter = otf.init_tf_vit(dim=192, depth=12, heads=h2, inter=i2, seed=3, stress=True)
+    want = otf.tf_vit_forward(sd, x, heads)
+    csd, kw = tf_vit_to_canonical(sd, heads)
+    m = _model(csd, **kw)
+    assert m.config.heads == h2 and m.config.intermediate == i2
+    _check(m(x.cuda()).logits, want, tol=3e-2)
+
+
+def test_batch_independence_and_chunking():
+    """Size-independent property: images are independent units -> any batch split gives identical logits."""
+    spec = ViTSpec.deit("tiny")
+    sd = ovit.state_dict_of(ovit.build_hf_model(spec, seed=0))
+    x = ovit.synthetic_images(37, seed=9).cuda()
+    m = _model(sd, max_batch=16)
+    a = m(x).logits
+    b = torch.cat([m(x[:5]).logits, m(x[5:]).logits])
+    assert torch.equal(a, b)
+    perm = torch.randperm(37, device="cuda")
+    assert torch.equal(m(x[perm]).logits, a[perm])

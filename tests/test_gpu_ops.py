@@ -1,0 +1,172 @@
+"""GPU parity tests of the op-level C ABI against plain torch fp32 references (same seeded inputs).
+
+Tolerances: bf16 operands + fp32 accumulation -> compare against the fp32 reference computed from the SAME
+bf16-rounded operands, so only accumulation order and the bf16 rounding of the output remain."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vit as ovit  # noqa: E402
+
+
+def _ops():
+    from edgevisiontransformer_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+@pytest.mark.parametrize("rows,D,eps", [(197, 192, 1e-12), (197 * 3 + 5, 384, 1e-12), (1000, 768, 1e-5),
+                                        (64, 64, 1e-5), (33, 576, 1e-5), (50, 147, 1e-5), (7, 1000, 1e-12)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_layernorm(rows, D, eps, out_dtype):
+    ops = _ops()
+    x = _rand((rows, D), 1, 2.0) + 0.5
+    g = 1 + _rand((D,), 2, 0.1)
+    b = _rand((D,), 3, 0.1)
+    y = ops.layernorm(x, g, b, eps, out_dtype=out_dtype)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, eps)
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 2e-5
+    assert (y.float() - ref).abs().max().item() < tol
+
+
+def test_layernorm_constant_row_and_writeback():
+    ops = _ops()
+    x = torch.full((4, 192), 3.25, device="cuda")
+    g = torch.ones(192, device="cuda")
+    b = torch.zeros(192, device="cuda")
+    y = ops.layernorm(x, g, b, 1e-12, out_dtype=torch.float32)
+    assert torch.isfinite(y).all() and y.abs().max().item() == 0.0      # centred variance: exactly 0, no NaN
+    x = _rand((10, 384), 4)
+    ref = torch.nn.functional.layer_norm(x, (384,), g.new_ones(384), g.new_zeros(384), 1e-5)
+    y = ops.layernorm(x, g.new_ones(384), g.new_zeros(384), 1e-5, write_back=True)
+    assert (x - ref).abs().max().item() < 2e-5 and (y.float() - ref).abs().max().item() < 2e-2
+
+
+def test_layernorm2d():
+    ops = _ops()
+    x = _rand((3, 197, 192), 5)
+    add = _rand((3, 197, 192), 6)
+    g = 1 + _rand((197, 192), 7, 0.1)
+    b = _rand((197, 192), 8, 0.1)
+    y = ops.layernorm2d(x, g, b, 1e-5, addend=add)
+    ref = torch.nn.functional.layer_norm(x + add, (197, 192), g, b, 1e-5)
+    assert (y - ref).abs().max().item() < 5e-5
+
+
+GEMM_SHAPES = [
+    # (M, N, K)  -- DeiT shapes, pruned widths, alignment cliffs from the reference's sweeps
+    (197, 576, 192), (197 * 4, 192, 192), (197 * 2, 768, 192), (197 * 2, 192, 768),
+    (394, 2304, 768), (300, 768, 3072), (256, 3072, 768),
+    (197, 192, 64), (197, 64, 192), (197, 230, 192), (197, 192, 230), (197, 231, 192),
+    (1, 1000, 192), (5, 1000, 768), (129, 160, 200), (128, 8, 8), (1000, 1, 64), (63, 3072, 768), (16, 32, 4096),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias(M, N, K):
+    ops = _ops()
+    lda, ldw = (K + 7) // 8 * 8, (K + 7) // 8 * 8
+    a = torch.zeros((M, lda), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((N, ldw), dtype=torch.bfloat16, device="cuda")
+    a[:, :K] = _rand((M, K), 1).bfloat16()
+    w[:, :K] = _rand((N, K), 2, 0.05).bfloat16()
+    if lda > K:   # garbage in the pad columns must be ignored (TMA zero fill past K)
+        a[:, K:] = 7.0
+        w[:, K:] = -3.0
+    bias = _rand((N,), 3, 0.1)
+    ref = a[:, :K].float() @ w[:, :K].float().t() + bias
+    out = ops.linear(a, w, bias, out_dtype=torch.float32, k=K)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, math.sqrt(K) * 0.05), f"f32-out err {err}"
+    outb = ops.linear(a, w, bias, out_dtype=torch.bfloat16, k=K)
+    errb = (outb.float() - ref).abs().max().item()
+    assert errb < 1e-2 * max(1.0, ref.abs().max().item()), f"bf16-out err {errb}"
+
+
+@pytest.mark.parametrize("act", ["gelu_erf", "gelu_tanh"])
+def test_gemm_gelu_and_residual(act):
+    ops = _ops()
+    M, N, K = 197 * 3, 768, 192
+    a = _rand((M, K), 1).bfloat16()
+    w = _rand((N, K), 2, 0.08).bfloat16()
+    bias = _rand((N,), 3, 0.2)
+    z = a.float() @ w.float().t() + bias
+    ref = ovit.gelu_erf(z) if act == "gelu_erf" else ovit.gelu_tanh(z)
+    out = ops.linear(a, w, bias, act=act, out_dtype=torch.float32)
+    assert (out - ref).abs().max().item() < 2e-3
+    # residual, in place: out aliases residual
+    res = _rand((M, N), 4)
+    want = z + res
+    got = ops.linear(a, w, bias, residual=res, out=res, out_dtype=torch.float32)
+    assert got.data_ptr() == res.data_ptr()
+    assert (res - want).abs().max().item() < 2e-3
+
+
+def test_gemm_tf32():
+    ops = _ops()
+    M, N, K = 197, 576, 192
+    a = _rand((M, K), 1)
+    w = _rand((N, K), 2, 0.05)
+    bias = _rand((N,), 3, 0.1)
+    ref = a @ w.t() + bias
+    out = ops.linear(a, w, bias, out_dtype=torch.float32)
+    assert (out - ref).abs().max().item() < 5e-3           # tf32: 10-bit mantissa operands
+
+
+def _attn_ref(qkv, B, S, heads, hs=64):
+    a = heads * hs
+    q, k, v = qkv[:, :a].float(), qkv[:, a:2 * a].float(), qkv[:, 2 * a:3 * a].float()
+    return ovit.attention(q.view(B, S, a), k.view(B, S, a), v.view(B, S, a), hs).reshape(B * S, a)
+
+
+@pytest.mark.parametrize("B,S,heads", [(2, 197, 3), (1, 198, 1), (3, 128, 2), (2, 40, 6), (1, 256, 2), (5, 197, 12), (2, 16, 1), (1, 1, 1)])
+def test_attention(B, S, heads):
+    ops = _ops()
+    qkv = _rand((B * S, 3 * heads * 64), 1, 1.0).bfloat16()
+    ctx = ops.attention(qkv, B, S, heads)
+    ref = _attn_ref(qkv, B, S, heads)
+    err = (ctx.float() - ref).abs().max().item()
+    assert err < 2e-2, f"attention err {err}"
+
+
+def test_attention_head_mask_and_peaky_scores():
+    ops = _ops()
+    B, S, heads = 2, 197, 3
+    qkv = _rand((B * S, 3 * heads * 64), 2, 3.0).bfloat16()       # large logits: softmax near one-hot
+    mask = torch.tensor([1.0, 0.0, 1.0], device="cuda")
+    ctx = ops.attention(qkv, B, S, heads, head_mask=mask)
+    ref = _attn_ref(qkv, B, S, heads).view(B * S, heads, 64) * mask.view(1, heads, 1)
+    assert (ctx.float() - ref.reshape(B * S, -1)).abs().max().item() < 6e-2
+    assert ctx.view(B * S, heads, 64)[:, 1].abs().max().item() == 0.0
+
+
+def test_im2col_and_cast_and_unfold():
+    ops = _ops()
+    x = _rand((3, 3, 224, 224), 1)
+    cols = ops.im2col_patch(x, 16)
+    ref = x.reshape(3, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(3 * 196, 768).bfloat16()
+    assert torch.equal(cols, ref)                                   # pure gather + RN rounding: bit exact
+    v = _rand((1003,), 2)
+    assert torch.equal(ops.cast_bf16(v), v.bfloat16())
+    from oracle import t2t as ot2t
+    img = _rand((2, 30, 30, 3), 3)
+    u = ops.unfold_nhwc(img, 7, 4, 2)
+    refu = ot2t.unfold_nhwc(img.cpu(), 7, 4, 2).reshape(-1, 147)
+    assert u.shape[1] == 152
+    assert torch.equal(u[:, :147].cpu(), refu.bfloat16()) and u[:, 147:].abs().max().item() == 0
+
+
+def test_errors_are_loud():
+    ops = _ops()
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-5)          # CPU tensor
+    a = torch.zeros((4, 12), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.linear(a[:, :9], a[:, :9], None)           # 24-byte rows: not a legal TMA leading dimension -> EVT_ERR_INVALID
