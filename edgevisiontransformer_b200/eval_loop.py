@@ -1,0 +1,124 @@
+"""Eval loop around the forward: the immediate caller of the hot path.
+
+Mirrors ``evaluate`` in the reference (deit_pruning/src/utils.py:151-228, are_16_heads/classifier_eval.py:22-108):
+DataLoader -> host->device copy -> ``model(images).logits`` -> argmax -> accuracy, with the per-rank counters
+summed to rank 0 when distributed.  B200-first changes: pinned host staging with the H2D copy of chunk i+1
+overlapped with the forward of chunk i on a second stream, and argmax on the GPU so only B int64 leave the
+device per batch instead of B x 1000 floats (the reference does ``logits.cpu().numpy()`` per batch).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Iterable, Optional
+
+import torch
+
+
+class PipelinedClassifier:
+    """Runs a B200ViTForImageClassification over a HOST batch in chunks, double-buffering the H2D copies."""
+
+    def __init__(self, model, chunk: int = 512):
+        self.model = model
+        self.chunk = int(chunk)
+        self.device = next(model.parameters()).device
+        c = model.config
+        self._bufs = [torch.empty((self.chunk, 3, c.image_size, c.image_size), dtype=torch.float32, device=self.device)
+                      for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._free = [torch.cuda.Event() for _ in range(2)]
+
+    @torch.no_grad()
+    def _run(self, host_pixels: torch.Tensor, want_logits: bool):
+        if host_pixels.is_cuda:
+            raise ValueError("PipelinedClassifier takes host tensors; call the model directly for device tensors")
+        B = host_pixels.shape[0]
+        c = self.model.config
+        main = torch.cuda.current_stream(self.device)
+        out = torch.empty((B, c.num_labels) if want_logits else (B,), dtype=torch.float32 if want_logits else torch.int64,
+                          device=self.device)
+        n = (B + self.chunk - 1) // self.chunk
+        for k in range(2):
+            self._free[k].record(main)
+        for i in range(n):
+            s, e = i * self.chunk, min(B, (i + 1) * self.chunk)
+            k = i & 1
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._free[k])          # buffer k no longer read by forward i-2
+                self._bufs[k][: e - s].copy_(host_pixels[s:e], non_blocking=True)
+                self._ready[k].record(self._copy_stream)
+            main.wait_event(self._ready[k])
+            lg = self.model(self._bufs[k][: e - s]).logits
+            if want_logits:
+                out[s:e] = lg
+            else:
+                out[s:e] = lg.argmax(dim=-1)
+            self._free[k].record(main)
+        return out
+
+    def logits(self, host_pixels: torch.Tensor) -> torch.Tensor:
+        """[B, num_labels] f32 on the HOST (synchronises)."""
+        return self._run(host_pixels, True).cpu()
+
+    def predict(self, host_pixels: torch.Tensor) -> torch.Tensor:
+        """argmax class ids [B] on the HOST; only 8 bytes per image cross PCIe on the way back."""
+        return self._run(host_pixels, False).cpu()
+
+
+def evaluate(eval_data: Iterable, model, eval_batch_size: int = 100, device=None, result: Optional[Dict] = None,
+             distributed: bool = False, num_workers: int = 0, chunk: int = 512) -> Dict[str, float]:
+    """Drop-in for deit_pruning/src/utils.py:151 ``evaluate`` (same result keys).
+
+    ``eval_data`` is a map-style dataset of (image, label) like the reference's ImageFolder, or any iterable of
+    already-batched (images, labels).  ``eval_loss`` keeps the reference's (odd) definition: the mean logit."""
+    from torch.utils.data import DataLoader, Dataset, DistributedSampler, SequentialSampler
+    import torch.distributed as dist
+
+    if isinstance(eval_data, Dataset):
+        sampler = DistributedSampler(eval_data) if distributed else SequentialSampler(eval_data)
+        loader = DataLoader(eval_data, sampler=sampler, batch_size=eval_batch_size, num_workers=num_workers, pin_memory=True)
+    else:
+        loader = eval_data
+    runner = PipelinedClassifier(model, chunk=min(chunk, max(1, eval_batch_size)))
+    dev = runner.device
+    correct = torch.zeros((), dtype=torch.int64, device=dev)
+    loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    n_examples, n_steps, inference_time = 0, 0, 0.0
+    for images, labels in loader:
+        t0 = time.time()
+        lg = runner._run(images if not images.is_cuda else images.cpu(), True)
+        pred = lg.argmax(dim=-1)
+        correct += (pred == labels.to(dev, non_blocking=True)).sum()
+        loss_sum += lg.double().mean()
+        torch.cuda.current_stream(dev).synchronize()
+        inference_time += time.time() - t0
+        n_examples += images.shape[0]
+        n_steps += 1
+    result = dict(result or {})
+    result["eval_loss"] = float(loss_sum.item()) / max(n_steps, 1)
+    result["eval_accuracy"] = float(correct.item()) / max(n_examples, 1)
+    result["inference_time"] = inference_time
+    if distributed and dist.is_available() and dist.is_initialized():
+        reduce_counters(result, dev)
+    return result
+
+
+def reduce_counters(result: Dict[str, float], device) -> Dict[str, float]:
+    """dist.reduce(SUM)->rank 0 then / world_size for each scalar, as deit_pruning/src/utils.py:221-226.
+    The only collective anywhere near the path, and it runs after the loop."""
+    import torch.distributed as dist
+    keys = sorted(result)
+    t = torch.tensor([float(result[k]) for k in keys], dtype=torch.float64,
+                     device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.reduce(t, 0, op=dist.ReduceOp.SUM)
+    t /= dist.get_world_size()
+    for k, v in zip(keys, t.tolist()):
+        result[k] = v
+    return result
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous batch-shard [lo, hi) of rank `rank`."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
