@@ -24,7 +24,8 @@ constexpr int BM = 128;
 constexpr int kStageRowBytes = 128;  // one swizzle row: 64 bf16 or 32 tf32 of K
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 192;
-constexpr int kStgLd = 33;
+constexpr int kStgRowBytes = 144;  // 128 B of payload + 16 B pad: conflict-free 16-byte accesses both ways
+constexpr int kStgWarpBytes = 32 * kStgRowBytes;
 
 template <int BN>
 struct Cfg {
@@ -33,7 +34,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
   static constexpr int kTmemCols = BN == 256 ? 512 : BN == 192 ? 512 : BN == 128 ? 256 : 128;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * kStgLd * 4;
+  static constexpr int kStagingBytes = kEpiWarps * kStgWarpBytes;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kBarBytes;
 };
@@ -48,27 +49,48 @@ struct GemmParams {
   int out_group, out_group_stride, out_group_off;
   int tiles_m, tiles_n, num_kb;
   int k_step;  // elements of K per stage (64 bf16 / 32 tf32)
+  int vec_ok;  // out / residual / bias allow 16-byte vector access
 };
 
+__device__ __forceinline__ long long map_out_row(const GemmParams& p, long long row) {
+  if (p.out_group <= 0) return row;
+  const long long g = row / p.out_group;
+  return g * p.out_group_stride + p.out_group_off + (row - g * p.out_group);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // erf via Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2 + 8 FMA-class ops.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
   const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erfv = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erfv);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);  // 0.5 x (1 + sign(x) erf|.|) = hx + |hx| erf_abs
 }
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) ; u = sqrt(2/pi) (x + 0.044715 x^3)
   const float u = x * fmaf(0.044715f * 0.7978845608028654f, x * x, 0.7978845608028654f);
-  const float e = exp2f(-2.0f * 1.4426950408889634f * u);
-  return __fdividef(x, 1.0f + e);
+  const float e = ex2_approx(-2.0f * 1.4426950408889634f * u);
+  return x * rcp_approx(1.0f + e);
 }
 template <int ACT, bool EXACT>
 __device__ __forceinline__ float apply_act(float v) {
@@ -90,7 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* staging = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kStagingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::kStages;
@@ -182,63 +204,160 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 0..3
-    float* stg = staging + warp * 32 * kStgLd;
+    // Each chunk is 128 bytes of output per row (64 bf16 / 32 f32 columns).  Thread == accumulator row while the
+    // bias / activation math runs on CH independent register values (full ILP); the converted chunk then goes
+    // through a padded per-warp smem tile so that 8 consecutive lanes write one contiguous 128-byte row segment.
+    constexpr int CH = OUT_F32 ? 32 : 64;
+    uint8_t* stg = reinterpret_cast<uint8_t*>(staging) + warp * kStgWarpBytes;
     int as = 0;
     uint32_t aphase = 0;
     const bool has_res = p.residual != nullptr;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * BM + warp * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
+      const int rows_here = min(32, p.M - m0);  // may be <= 0 for a fully out-of-range warp
+      // Residual rows of this warp's 32x32 chunk, one float4 per (4-row group, lane): issued one chunk ahead so
+      // the HBM latency of the skip connection hides behind the previous chunk (and behind the MMA wait).
+      float4 rnext[8];
+      auto load_res = [&](int n0c) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          rnext[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < rows_here && p.vec_ok && n0c + CH <= p.N) {
+            const long long row = m0 + rr;
+            const long long rrow = p.res_row_mod > 0 ? p.res_row_off + row % p.res_row_mod : map_out_row(p, row);
+            rnext[it] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n0c + (lane & 7) * 4);
+          }
+        }
+      };
+      if constexpr (OUT_F32) {
+        if (has_res) load_res(nt0);
+      }
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + as * BN;
-      const int rows_here = min(32, p.M - m0);  // may be <= 0 for a fully out-of-range warp
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = nt0 + c * 32;
+      for (int c = 0; c < BN / CH; ++c) {
+        const int n0 = nt0 + c * CH;
         if (n0 >= p.N) break;
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_row + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (rows_here > 0) {
+        float v[CH];
+        {
+          uint32_t r[32];
+          ptx::tmem_ld_x32(t_row + c * CH, r);
+          if constexpr (CH == 64) {
+            uint32_t r2[32];
+            ptx::tmem_ld_x32(t_row + c * CH + 32, r2);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * kStgLd + j] = __uint_as_float(r[j]);
-          __syncwarp();
-          const int col = n0 + lane;
-          const bool colok = col < p.N;
-          const float b = (p.bias != nullptr && colok) ? __ldg(p.bias + col) : 0.0f;
-          // incremental row bookkeeping (no per-row division)
-          int grp = 0, pos = 0, rpos = 0;
-          if (p.out_group > 0) {
-            grp = m0 / p.out_group;
-            pos = m0 - grp * p.out_group;
+            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r2[j]);
+          } else {
+            ptx::tmem_ld_wait();
           }
-          if (p.res_row_mod > 0) rpos = m0 % p.res_row_mod;
-          for (int rr = 0; rr < rows_here; ++rr) {
-            const long long row = m0 + rr;
-            long long orow = row;
-            if (p.out_group > 0) {
-              orow = static_cast<long long>(grp) * p.out_group_stride + p.out_group_off + pos;
-              if (++pos == p.out_group) {
-                pos = 0;
-                ++grp;
-              }
-            }
-            float v = stg[rr * kStgLd + lane] + b;
-            v = apply_act<ACT, TF32>(v);
-            if (colok) {
-              if (has_res) {
-                long long rrow = orow;
-                if (p.res_row_mod > 0) rrow = p.res_row_off + rpos;
-                v += p.residual[rrow * p.ldr + col];
-              }
-              if (OUT_F32) reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = v;
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + col] = __float2bfloat16_rn(v);
-            }
-            if (p.res_row_mod > 0 && ++rpos == p.res_row_mod) rpos = 0;
-          }
-          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
+        if (rows_here <= 0) continue;
+        const bool full = p.vec_ok && (n0 + CH <= p.N);
+        float4 rcur[8];
+        if constexpr (OUT_F32) {
+          if (has_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
+            if (c + 1 < BN / CH && n0 + CH < p.N) load_res(n0 + CH);
+          }
+        }
+        if (p.bias != nullptr) {
+          if (full) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] += b.x;
+              v[4 * i + 1] += b.y;
+              v[4 * i + 2] += b.z;
+              v[4 * i + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = apply_act<ACT, TF32>(v[j]);
+        if constexpr (!OUT_F32) if (has_res && lane < rows_here) {  // rare combination: add before rounding to bf16
+          const long long orow = map_out_row(p, m0 + lane);
+          const long long rrow = p.res_row_mod > 0 ? p.res_row_off + (m0 + lane) % p.res_row_mod : orow;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n0 + j < p.N) v[j] += p.residual[rrow * p.ldr + n0 + j];
+        }
+        // stage: row-per-thread -> padded smem tile
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * kStgRowBytes + i * 16) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+            w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * kStgRowBytes + i * 16) = w;
+          }
+        }
+        __syncwarp();
+        // store: lanes 8k..8k+7 cover one 128-byte row segment; 4 rows per instruction
+        const int piece = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          if (rr < rows_here) {
+            const long long row = m0 + rr;
+            const long long orow = map_out_row(p, row);
+            if constexpr (OUT_F32) {
+              float4 val = *reinterpret_cast<const float4*>(stg + rr * kStgRowBytes + piece * 16);
+              const int col = n0 + piece * 4;
+              float* dst = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
+              if (full) {
+                if (has_res) {
+                  const float4 rs = rcur[it];
+                  val.x += rs.x;
+                  val.y += rs.y;
+                  val.z += rs.z;
+                  val.w += rs.w;
+                }
+                *reinterpret_cast<float4*>(dst) = val;
+              } else {
+                const float e[4] = {val.x, val.y, val.z, val.w};
+                const long long rrow = p.res_row_mod > 0 ? p.res_row_off + row % p.res_row_mod : orow;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (col + q < p.N) dst[q] = e[q] + (has_res ? p.residual[rrow * p.ldr + col + q] : 0.f);
+              }
+            } else {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRowBytes + piece * 16);
+              const int col = n0 + piece * 8;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col;
+              if (full) {
+                *reinterpret_cast<uint4*>(dst) = val;
+              } else {
+                const uint32_t e[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (col + q < p.N) {
+                    const uint16_t h = static_cast<uint16_t>(e[q >> 1] >> ((q & 1) * 16));
+                    reinterpret_cast<uint16_t*>(dst)[q] = h;
+                  }
+              }
+            }
+          }
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -351,6 +470,13 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
   p.tiles_n = (N + bn - 1) / bn;
   p.num_kb = (K + k_step - 1) / k_step;
   p.k_step = k_step;
+  {
+    const int oe = out_dtype == EVT_F32 ? 4 : 2;
+    bool ok = reinterpret_cast<uintptr_t>(out) % 16 == 0 && (ldo * oe) % 16 == 0;
+    if (bias) ok = ok && reinterpret_cast<uintptr_t>(bias) % 16 == 0;
+    if (residual) ok = ok && reinterpret_cast<uintptr_t>(residual) % 16 == 0 && (ldr * 4) % 16 == 0;
+    p.vec_ok = ok ? 1 : 0;
+  }
   const bool of32 = out_dtype == EVT_F32;
 #define EVT_BN_CASE(BNV)                                                                        \
   case BNV:                                                                                     \
