@@ -25,18 +25,20 @@ constexpr int kStageRowBytes = 128;  // one swizzle row: 64 bf16 or 32 tf32 of K
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 192;
 constexpr int kStgRowBytes = 144;  // 128 B of payload + 16 B pad: conflict-free 16-byte accesses both ways
-constexpr int kStgWarpBytes = 32 * kStgRowBytes;
+constexpr int kStgWarpBytes = 32 * kStgRowBytes;  // generic path: one padded 32-row tile per warp
+constexpr int kTmaStgBytes = 32 * 128;            // TMA path: dense 128-byte rows, 128B-swizzled, two per warp
 
 template <int BN>
 struct Cfg {
   static constexpr int kABytes = BM * kStageRowBytes;
   static constexpr int kBBytes = BN * kStageRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
+  static constexpr int kStages = BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
   static constexpr int kTmemCols = BN == 256 ? 512 : BN == 192 ? 512 : BN == 128 ? 256 : 128;
-  static constexpr int kStagingBytes = kEpiWarps * kStgWarpBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 2 * kTmaStgBytes;  // >= kEpiWarps * kStgWarpBytes
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kBarBytes;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 struct GemmParams {
@@ -105,9 +107,10 @@ __device__ __forceinline__ float apply_act(float v) {
   return v;
 }
 
-template <int BN, bool TF32, bool OUT_F32, int ACT>
+template <int BN, bool TF32, bool OUT_F32, int ACT, bool TMA_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+            const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,6 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
+    if (TMA_OUT) ptx::prefetch_tmap(&tmO);
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -208,7 +212,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // bias / activation math runs on CH independent register values (full ILP); the converted chunk then goes
     // through a padded per-warp smem tile so that 8 consecutive lanes write one contiguous 128-byte row segment.
     constexpr int CH = OUT_F32 ? 32 : 64;
-    uint8_t* stg = reinterpret_cast<uint8_t*>(staging) + warp * kStgWarpBytes;
+    uint8_t* stg = staging + warp * (TMA_OUT ? 2 * kTmaStgBytes : kStgWarpBytes);
+    int buf = 0;
     int as = 0;
     uint32_t aphase = 0;
     const bool has_res = p.residual != nullptr;
@@ -231,7 +236,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       };
-      if constexpr (OUT_F32) {
+      if constexpr (OUT_F32 && !TMA_OUT) {
         if (has_res) load_res(nt0);
       }
       ptx::mbar_wait(&tfull[as], aphase);
@@ -260,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (rows_here <= 0) continue;
         const bool full = p.vec_ok && (n0 + CH <= p.N);
         float4 rcur[8];
-        if constexpr (OUT_F32) {
+        if constexpr (OUT_F32 && !TMA_OUT) {
           if (has_res) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
@@ -292,6 +297,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < CH; ++j)
             if (n0 + j < p.N) v[j] += p.residual[rrow * p.ldr + n0 + j];
+        }
+        if constexpr (TMA_OUT) {
+          // dense 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7) exactly as the tensor map expects:
+          // conflict-free stores, and the TMA engine does the coalescing, the M/N clipping and (for the skip
+          // connection) the f32 add into the residual stream at L2 -- the SM never reads the residual.
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = stg + buf * kTmaStgBytes + lane * 128;
+          const int sw = lane & 7;
+          if constexpr (OUT_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(sb + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+              w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              *reinterpret_cast<uint4*>(sb + ((i ^ sw) << 4)) = w;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (has_res) ptx::tma_reduce_add_2d(&tmO, stg + buf * kTmaStgBytes, n0, m0);
+            else ptx::tma_store_2d(&tmO, stg + buf * kTmaStgBytes, n0, m0);
+            ptx::bulk_commit();
+          }
+          buf ^= 1;
+          continue;
         }
         // stage: row-per-thread -> padded smem tile
         if constexpr (OUT_F32) {
@@ -367,6 +405,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         aphase ^= 1;
       }
     }
+    if (TMA_OUT && lane == 0) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();
@@ -391,10 +430,10 @@ int choose_bn(int N) {
   return best;
 }
 
-template <int BN, bool TF32, bool OUT_F32, int ACT>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t stream) {
+template <int BN, bool TF32, bool OUT_F32, int ACT, bool TMA_OUT>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
-  auto kern = gemm_kernel<BN, TF32, OUT_F32, ACT>;
+  auto kern = gemm_kernel<BN, TF32, OUT_F32, ACT, TMA_OUT>;
   static bool configured = false;  // per instantiation; attribute is per-device-context but identical everywhere
   static int configured_dev = -1;
   int dev = 0;
@@ -406,24 +445,25 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, 
   }
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, p);
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
   EVT_LAUNCH_CHECK("gemm_kernel");
   return EVT_OK;
 }
 
-template <int BN, bool TF32>
-int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& p, bool out_f32, int act, cudaStream_t s) {
+template <int BN, bool TF32, bool TMA_OUT>
+int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o, const GemmParams& p, bool out_f32, int act,
+                 cudaStream_t s) {
   if (out_f32) {
     switch (act) {
-      case EVT_ACT_NONE: return launch<BN, TF32, true, EVT_ACT_NONE>(a, w, p, s);
-      case EVT_ACT_GELU_ERF: return launch<BN, TF32, true, EVT_ACT_GELU_ERF>(a, w, p, s);
-      default: return launch<BN, TF32, true, EVT_ACT_GELU_TANH>(a, w, p, s);
+      case EVT_ACT_NONE: return launch<BN, TF32, true, EVT_ACT_NONE, TMA_OUT>(a, w, o, p, s);
+      case EVT_ACT_GELU_ERF: return launch<BN, TF32, true, EVT_ACT_GELU_ERF, TMA_OUT>(a, w, o, p, s);
+      default: return launch<BN, TF32, true, EVT_ACT_GELU_TANH, TMA_OUT>(a, w, o, p, s);
     }
   }
   switch (act) {
-    case EVT_ACT_NONE: return launch<BN, TF32, false, EVT_ACT_NONE>(a, w, p, s);
-    case EVT_ACT_GELU_ERF: return launch<BN, TF32, false, EVT_ACT_GELU_ERF>(a, w, p, s);
-    default: return launch<BN, TF32, false, EVT_ACT_GELU_TANH>(a, w, p, s);
+    case EVT_ACT_NONE: return launch<BN, TF32, false, EVT_ACT_NONE, TMA_OUT>(a, w, o, p, s);
+    case EVT_ACT_GELU_ERF: return launch<BN, TF32, false, EVT_ACT_GELU_ERF, TMA_OUT>(a, w, o, p, s);
+    default: return launch<BN, TF32, false, EVT_ACT_GELU_TANH, TMA_OUT>(a, w, o, p, s);
   }
 }
 
@@ -478,10 +518,24 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
     p.vec_ok = ok ? 1 : 0;
   }
   const bool of32 = out_dtype == EVT_F32;
-#define EVT_BN_CASE(BNV)                                                                        \
-  case BNV:                                                                                     \
-    return tf32 ? dispatch_epi<BNV, true>(tmA, tmW, p, of32, act, stream)                       \
-                : dispatch_epi<BNV, false>(tmA, tmW, p, of32, act, stream);
+  // TMA epilogue: contiguous output rows, 16-byte aligned, and the skip connection (if any) updated in place
+  const int oeb = of32 ? 4 : 2;
+  const bool tma_out = out_group == 0 && res_row_mod == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                       (ldo * oeb) % 16 == 0 &&
+                       (residual == nullptr || (of32 && residual == reinterpret_cast<const float*>(out) && ldr == ldo));
+  CUtensorMap tmO = tmA;
+  if (tma_out) {
+    rc = make_tmap_2d(&tmO, out, oeb, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo), 32,
+                      128 / oeb);
+    if (rc != EVT_OK) return rc;
+  }
+#define EVT_BN_CASE(BNV)                                                                                   \
+  case BNV:                                                                                                \
+    if (tma_out)                                                                                           \
+      return tf32 ? dispatch_epi<BNV, true, true>(tmA, tmW, tmO, p, of32, act, stream)                     \
+                  : dispatch_epi<BNV, false, true>(tmA, tmW, tmO, p, of32, act, stream);                   \
+    return tf32 ? dispatch_epi<BNV, true, false>(tmA, tmW, tmO, p, of32, act, stream)                      \
+                : dispatch_epi<BNV, false, false>(tmA, tmW, tmO, p, of32, act, stream);
   switch (bn) {
     EVT_BN_CASE(256)
     EVT_BN_CASE(192)
