@@ -114,37 +114,68 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int nchunk = p.SK / 16;
     ptx::mbar_wait(bar_s, 0);
     ptx::tc_fence_after();
-    // pass 1: row max over the valid keys
-    float m = -CUDART_INF_F;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[16];
-      ptx::tmem_ld_x16(t_row + c * 16, r);
-      ptx::tmem_ld_wait();
+    // Warps whose 32 query rows are all past the sequence end (rows 224..255 of the second tile when S = 197)
+    // skip the softmax arithmetic; their P / O lanes hold garbage that is never stored.
+    const bool warp_live = mt * kQRows + warp * 32 < p.S;
+    float sum = 1.f;
+    if (warp_live) {
+      const int nfull = p.S / 16;  // chunks with no masked key
+      // pass 1: row max over the valid keys
+      float m = -CUDART_INF_F;
+      for (int c = 0; c < nfull; ++c) {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_row + c * 16, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c * 16 + j < p.S) m = fmaxf(m, __uint_as_float(r[j]));
-    }
-    // pass 2: probabilities (bf16) written over the S columns already consumed, row sum of the rounded values
-    const float msl = m * p.scale_log2e;
-    float sum = 0.f;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[16];
-      ptx::tmem_ld_x16(t_row + c * 16, r);
-      ptx::tmem_ld_wait();
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const int key = c * 16 + j;
-        float p0 = key < p.S ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl)) : 0.f;
-        float p1 = key + 1 < p.S ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl)) : 0.f;
-        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-        const float2 back = __bfloat1622float2(hb);
-        sum += back.x + back.y;
-        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[j]));
       }
-      ptx::tmem_st_x8(t_row + c * 8, pk);
+      if (nfull < nchunk) {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_row + nfull * 16, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nfull * 16 + j < p.S) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+      // pass 2: probabilities (bf16) written over the S columns already consumed; fp32 row sum
+      const float msl = m * p.scale_log2e;
+      float s0 = 0.f, s1 = 0.f;
+      for (int c = 0; c < nfull; ++c) {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_row + c * 16, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl));
+          s0 += p0;
+          s1 += p1;
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        ptx::tmem_st_x8(t_row + c * 8, pk);
+      }
+      if (nfull < nchunk) {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_row + nfull * 16, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const int key = nfull * 16 + j;
+          const float p0 = key < p.S ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl)) : 0.f;
+          const float p1 = key + 1 < p.S ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl)) : 0.f;
+          s0 += p0;
+          s1 += p1;
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        ptx::tmem_st_x8(t_row + nfull * 8, pk);
+      }
+      sum = s0 + s1;
+      ptx::tmem_st_wait();
     }
-    ptx::tmem_st_wait();
     ptx::tc_fence_before();
     ptx::mbar_arrive(bar_p);
     // epilogue: O / sum
