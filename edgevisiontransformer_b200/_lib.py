@@ -17,6 +17,7 @@ EVT_OK, EVT_ERR_INVALID, EVT_ERR_CUDA, EVT_ERR_UNSUPPORTED, EVT_ERR_STATE = 0, -
 EVT_F32, EVT_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
 DIALECT_HF, DIALECT_TF = 0, 1
+PREC_BF16, PREC_TF32 = 0, 1
 MAX_LAYERS = 64
 
 
@@ -26,7 +27,7 @@ class ModelSpec(C.Structure):
         ("image", C.c_int), ("patch", C.c_int), ("head_size", C.c_int), ("num_labels", C.c_int),
         ("act", C.c_int), ("eps", C.c_float),
         ("heads", C.c_int * MAX_LAYERS), ("inter", C.c_int * MAX_LAYERS),
-        ("final_ln", C.c_int), ("head_hidden", C.c_int), ("t2t", C.c_int),
+        ("final_ln", C.c_int), ("head_hidden", C.c_int), ("t2t", C.c_int), ("precision", C.c_int),
     ]
 
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     "evt_gemm_bias_act": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _p, _i, _i64, _i, _i, _i, _i64, _i, _i, _i, _p]),
     "evt_gemm_bias_act_tf32": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _p, _i64, _i, _i, _i, _i64, _i, _i, _i, _p]),
     "evt_attention_fwd": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _p]),
+    "evt_attention_fwd_tf32": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _p]),
     "evt_im2col_patch": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "evt_prefix_tokens": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "evt_cast_f32_bf16": (_i, [_p, _p, _i64, _p]),

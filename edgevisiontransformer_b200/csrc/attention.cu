@@ -216,6 +216,187 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// tf32 accuracy mode: Q, K, V and the context are fp32 in HBM; the tensor core reads them as tf32 (kind::tf32,
+// K = 8 per MMA) and accumulates in fp32.  A 64-float head row is two 128-byte swizzle atoms, so Q and K are
+// loaded as two TMA boxes of 32 columns each.  V is needed as the B operand of O = P V with the KEY index
+// contiguous; instead of an MN-major 32-bit descriptor the softmax warps transpose V from global memory into
+// K-major 128B-swizzled atoms (64 rows of d x 32 keys) while the TMA / S = Q K^T pipeline is in flight.
+// P stays fp32 and overwrites S column for column; O has its own 64 TMEM columns (512 allocated -> one CTA
+// per SM; this mode serves the small-batch / 1e-3 tolerance path).  SK is S rounded up to 32 here.
+constexpr int kTmemColsTf32 = 512;
+constexpr int kOColTf32 = 256;
+
+struct AttnParamsTf32 {
+  const float* qkv;
+  float* ctx;
+  const float* head_mask;
+  long long ldq, ldc;
+  long long total_rows;
+  int S, SK, heads;
+  float scale_log2e;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const AttnParamsTf32 p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int k_atom = p.SK * 128;   // one 32-column atom of K
+  const int n_vt = p.SK / 32;      // V^T atoms: 64 rows (d) x 32 keys, 8 KB each
+  uint8_t* sQ = smem;              // 2 atoms x 128 rows x 128 B
+  uint8_t* sK = sQ + 2 * kQRows * 128;
+  uint8_t* sVT = sK + 2 * k_atom;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sVT + n_vt * 8192);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int a = p.heads * kHD;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK);
+      ptx::mbar_init(bar_load, 1);
+      ptx::mbar_init(bar_s, 1);
+      ptx::mbar_init(bar_p, 128);
+      ptx::mbar_init(bar_o, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemColsTf32>(tmem_ptr);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int row0 = b * p.S;
+      ptx::mbar_arrive_expect_tx(bar_load, 2 * kQRows * 128 + 2 * k_atom);
+      for (int t = 0; t < 2; ++t) {
+        ptx::tma_load_2d(sQ + t * kQRows * 128, &tmQ, bar_load, h * kHD + t * 32, row0 + mt * kQRows);
+        ptx::tma_load_2d(sK + t * k_atom, &tmK, bar_load, a + h * kHD + t * 32, row0);
+      }
+      ptx::mbar_wait(bar_load, 0);
+      ptx::tc_fence_after();
+      {  // S = Q K^T : 2 atoms x 4 MMAs of K = 8
+        const uint32_t idesc = ptx::make_idesc(kQRows, p.SK, 2, 0, 0);
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(sQ + t * kQRows * 128));
+          const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK + t * k_atom));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::mma_tf32_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(bar_s);
+      }
+      ptx::mbar_wait(bar_p, 0);
+      ptx::tc_fence_after();
+      {  // O = P V : P (fp32 read as tf32) from TMEM, 8 columns per MMA; V^T K-major atoms of 32 keys
+        const uint32_t idesc = ptx::make_idesc(kQRows, kHD, 2, 0, 0);
+        for (int j = 0; j < n_vt; ++j) {
+          const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sVT + j * 8192));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_tf32_ts(tmem_base + kOColTf32, tmem_base + j * 32 + k * 8, vd + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(bar_o);
+      }
+    }
+  } else {
+    // ---- transpose V (keys x 64) from global into K-major swizzled atoms: thread == key
+    {
+      const int tid = threadIdx.x;  // 0..127
+      for (int key = tid; key < p.SK; key += 128) {
+        const long long grow = static_cast<long long>(b) * p.S + key;
+        const bool ok = grow < p.total_rows;  // rows past the sequence end are multiplied by P = 0; just keep them finite
+        const float* src = p.qkv + grow * p.ldq + 2 * a + h * kHD;
+        uint8_t* atom = sVT + (key >> 5) * 8192;
+        const int kc = (key & 31) >> 2, ke = (key & 3) * 4;
+#pragma unroll
+        for (int d4 = 0; d4 < 16; ++d4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v = *reinterpret_cast<const float4*>(src + d4 * 4);
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = d4 * 4 + q;
+            *reinterpret_cast<float*>(atom + d * 128 + ((kc ^ (d & 7)) << 4) + ke) = ptx::round_tf32(e[q]);
+          }
+        }
+      }
+    }
+    const int qrow = mt * kQRows + warp * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int nchunk = p.SK / 16;
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    float m = -CUDART_INF_F;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(t_row + c * 16, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < p.S) m = fmaxf(m, __uint_as_float(r[j]));
+    }
+    const float msl = m * p.scale_log2e;
+    float sum = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(t_row + c * 16, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        // exp2f (not the approx intrinsic): this mode is the accuracy path
+        float pv = c * 16 + j < p.S ? exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl)) : 0.f;
+        pv = ptx::round_tf32(pv);  // the value the tensor core will actually use (it would truncate otherwise)
+        sum += pv;
+        r[j] = __float_as_uint(pv);
+      }
+      ptx::tmem_st_x16(t_row + c * 16, r);
+    }
+    ptx::tmem_st_wait();
+    ptx::fence_proxy_async_smem();  // V^T written with ordinary stores, read by the tensor core
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(bar_p);
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    float inv = 1.0f / sum;
+    if (p.head_mask != nullptr) inv *= p.head_mask[h];
+    const bool valid = qrow < p.S;
+    float* dst = p.ctx + (static_cast<long long>(b) * p.S + qrow) * p.ldc + h * kHD;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      ptx::tmem_ld_x32(t_row + kOColTf32 + half * 32, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + half * 32 + j) =
+              make_float4(ptx::round_tf32(__uint_as_float(r[j]) * inv), ptx::round_tf32(__uint_as_float(r[j + 1]) * inv),
+                          ptx::round_tf32(__uint_as_float(r[j + 2]) * inv), ptx::round_tf32(__uint_as_float(r[j + 3]) * inv));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemColsTf32>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
@@ -256,6 +437,48 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   return EVT_OK;
 }
 
+int attention_tf32_launch(const float* qkv, int64_t ldq, float* ctx, int64_t ldc, const float* head_mask, int B, int S,
+                          int heads, int head_size, float scale, cudaStream_t stream) {
+  EVT_CHECK_ARG(qkv && ctx, "attention_tf32: null pointer");
+  EVT_CHECK_ARG(B > 0 && S > 0 && heads > 0, "attention_tf32: B, S, heads must be positive");
+  if (head_size != kHD) return fail(EVT_ERR_UNSUPPORTED, "attention_tf32: only head size 64 is implemented");
+  if (S > 256) return fail(EVT_ERR_UNSUPPORTED, "attention_tf32: sequence length above 256 is not implemented");
+  EVT_CHECK_ARG(ldq >= 3ll * heads * kHD && ldc >= static_cast<int64_t>(heads) * kHD, "attention_tf32: leading dimension too small");
+  EVT_CHECK_ARG(ldc % 4 == 0 && reinterpret_cast<uintptr_t>(ctx) % 16 == 0, "attention_tf32: ctx must be 16-byte aligned rows");
+  EVT_CHECK_ARG(ldq % 4 == 0 && reinterpret_cast<uintptr_t>(qkv) % 16 == 0, "attention_tf32: qkv must be 16-byte aligned rows");
+  const int SK = (S + 31) / 32 * 32;
+  CUtensorMap tmQ, tmKV;
+  const uint64_t rows = static_cast<uint64_t>(B) * S;
+  int rc = make_tmap_2d(&tmQ, qkv, 4, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), kQRows, 32);
+  if (rc != EVT_OK) return rc;
+  rc = make_tmap_2d(&tmKV, qkv, 4, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), SK, 32);
+  if (rc != EVT_OK) return rc;
+  AttnParamsTf32 p;
+  p.qkv = qkv;
+  p.ldq = ldq;
+  p.total_rows = static_cast<long long>(rows);
+  p.ctx = ctx;
+  p.head_mask = head_mask;
+  p.ldc = ldc;
+  p.S = S;
+  p.SK = SK;
+  p.heads = heads;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  const int smem = 1024 + 2 * kQRows * 128 + 2 * SK * 128 + (SK / 32) * 8192 + 64;
+  static int configured_dev = -1;
+  int dev = 0;
+  EVT_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    EVT_CUDA(cudaFuncSetAttribute(attention_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  1024 + 2 * kQRows * 128 + 2 * 256 * 128 + 8 * 8192 + 64));
+    configured_dev = dev;
+  }
+  dim3 grid((S + kQRows - 1) / kQRows, heads, B);
+  attention_tf32_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmKV, p);
+  EVT_LAUNCH_CHECK("attention_tf32_kernel");
+  return EVT_OK;
+}
+
 }  // namespace evt
 
 extern "C" int evt_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B,
@@ -264,4 +487,13 @@ extern "C" int evt_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_
   if (rc != EVT_OK) return rc;
   return evt::attention_launch(qkv, ldq, ctx, ldc, head_mask, B, S, heads, head_size, scale,
                                static_cast<cudaStream_t>(stream));
+}
+
+// tf32 accuracy mode: qkv and ctx are f32.
+extern "C" int evt_attention_fwd_tf32(const float* qkv, int64_t ldq, float* ctx, int64_t ldc, const float* head_mask,
+                                      int B, int S, int heads, int head_size, float scale, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::attention_tf32_launch(qkv, ldq, ctx, ldc, head_mask, B, S, heads, head_size, scale,
+                                    static_cast<cudaStream_t>(stream));
 }

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace evt {
 namespace {
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict
   const int gw = W / P, gh = H / P;
   const long long row = (static_cast<long long>(b) * gh + py) * gw + pxi;
   const int k = (c * P + i) * P + j;
-  *reinterpret_cast<float4*>(cols + row * (3ll * P * P) + k) = v;
+  *reinterpret_cast<float4*>(cols + row * (3ll * P * P) + k) =
+      make_float4(ptx::round_tf32(v.x), ptx::round_tf32(v.y), ptx::round_tf32(v.z), ptx::round_tf32(v.w));
 }
 
 __global__ void __launch_bounds__(256) prefix_tokens_kernel(const float* __restrict__ prefix,

@@ -52,6 +52,7 @@ struct GemmParams {
   int tiles_m, tiles_n, num_kb;
   int k_step;  // elements of K per stage (64 bf16 / 32 tf32)
   int vec_ok;  // out / residual / bias allow 16-byte vector access
+  int round_tf32;  // f32 output feeds a tf32 tensor-core op: round to nearest tf32 when written
 };
 
 __device__ __forceinline__ long long map_out_row(const GemmParams& p, long long row) {
@@ -291,6 +292,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = apply_act<ACT, TF32>(v[j]);
+        if constexpr (OUT_F32) {
+          if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = ptx::round_tf32(v[j]);
+          }
+        }
         if constexpr (!OUT_F32) if (has_res && lane < rows_here) {  // rare combination: add before rounding to bf16
           const long long orow = map_out_row(p, m0 + lane);
           const long long rrow = p.res_row_mod > 0 ? p.res_row_off + (m0 + lane) % p.res_row_mod : orow;
@@ -478,7 +485,8 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
   EVT_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive");
   EVT_CHECK_ARG(M < (1ll << 31) - 256, "gemm: M too large");
   EVT_CHECK_ARG(in_dtype == EVT_BF16 || in_dtype == EVT_F32, "gemm: input dtype must be bf16 or f32(tf32)");
-  EVT_CHECK_ARG(out_dtype == EVT_BF16 || out_dtype == EVT_F32, "gemm: out dtype must be bf16 or f32");
+  EVT_CHECK_ARG(out_dtype == EVT_BF16 || out_dtype == EVT_F32 || out_dtype == EVT_TF32, "gemm: out dtype must be bf16, f32 or tf32");
+  EVT_CHECK_ARG(!(out_dtype == EVT_TF32 && residual != nullptr), "gemm: a tf32-rounded output cannot take a residual");
   EVT_CHECK_ARG(act >= EVT_ACT_NONE && act <= EVT_ACT_GELU_TANH, "gemm: unknown activation");
   EVT_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "gemm: leading dimension smaller than the row length");
   EVT_CHECK_ARG(out_group >= 0 && res_row_mod >= 0, "gemm: negative row-group parameter");
@@ -511,13 +519,14 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
   p.num_kb = (K + k_step - 1) / k_step;
   p.k_step = k_step;
   {
-    const int oe = out_dtype == EVT_F32 ? 4 : 2;
+    const int oe = out_dtype != EVT_BF16 ? 4 : 2;
     bool ok = reinterpret_cast<uintptr_t>(out) % 16 == 0 && (ldo * oe) % 16 == 0;
     if (bias) ok = ok && reinterpret_cast<uintptr_t>(bias) % 16 == 0;
     if (residual) ok = ok && reinterpret_cast<uintptr_t>(residual) % 16 == 0 && (ldr * 4) % 16 == 0;
     p.vec_ok = ok ? 1 : 0;
   }
-  const bool of32 = out_dtype == EVT_F32;
+  const bool of32 = out_dtype != EVT_BF16;
+  p.round_tf32 = out_dtype == EVT_TF32 ? 1 : 0;
   // TMA epilogue: contiguous output rows, 16-byte aligned, and the skip connection (if any) updated in place
   const int oeb = of32 ? 4 : 2;
   const bool tma_out = out_group == 0 && res_row_mod == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace evt {
 namespace {
@@ -16,7 +17,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // D even, D <= 1024, strides even.  NV = ceil(D / 64).
-template <int NV, bool OUT_BF16>
+template <int NV, int OUT>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long x_stride,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       void* __restrict__ y, long long y_stride, float* y_copy,
@@ -54,9 +55,13 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
     if (c < D) {
       const float2 g = *reinterpret_cast<const float2*>(gamma + c);
       const float2 b = *reinterpret_cast<const float2*>(beta + c);
-      const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
-      const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
-      if (OUT_BF16) {
+      float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+      float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      if (OUT == EVT_TF32) {
+        o0 = ptx::round_tf32(o0);
+        o1 = ptx::round_tf32(o1);
+      }
+      if (OUT == EVT_BF16) {
         __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
         *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(y) + row * y_stride + c) = h;
       } else {
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
 }
 
 // Any D (odd, > 1024): warp per row, three strided passes over the row (L1/L2 resident).
-template <bool OUT_BF16>
+template <int OUT>
 __global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, long long x_stride,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, void* __restrict__ y,
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, lo
   }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
   for (int c = lane; c < D; c += 32) {
-    const float o = (xr[c] - mean) * rstd * gamma[c] + beta[c];
-    if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[row * y_stride + c] = __float2bfloat16_rn(o);
+    float o = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if (OUT == EVT_TF32) o = ptx::round_tf32(o);
+    if (OUT == EVT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[row * y_stride + c] = __float2bfloat16_rn(o);
     else reinterpret_cast<float*>(y)[row * y_stride + c] = o;
     if (y_copy != nullptr) y_copy[row * x_stride + c] = o;
   }
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(1024) ln2d_kernel(const float* __restrict__ x,
   }
 }
 
-template <bool OUT_BF16>
+template <int OUT>
 int launch_rows(const float* x, long long xs, const float* g, const float* b, void* y, long long ys, float* yc,
                 long long rows, int D, float eps, cudaStream_t st) {
   const int wpb = 8;
@@ -142,12 +148,12 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
                     (reinterpret_cast<uintptr_t>(g) % 8 == 0) && (reinterpret_cast<uintptr_t>(b) % 8 == 0) &&
                     (yc == nullptr || reinterpret_cast<uintptr_t>(yc) % 8 == 0);
   if (!fast) {
-    ln_rows_generic_kernel<OUT_BF16><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps);
+    ln_rows_generic_kernel<OUT><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps);
   } else {
     const int nv = (D + 63) / 64;
 #define EVT_LN_CASE(NVV)                                                                          \
   case NVV:                                                                                       \
-    ln_rows_kernel<NVV, OUT_BF16><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps); \
+    ln_rows_kernel<NVV, OUT><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps); \
     break;
     switch (nv) {
       EVT_LN_CASE(1) EVT_LN_CASE(2) EVT_LN_CASE(3) EVT_LN_CASE(4) EVT_LN_CASE(5) EVT_LN_CASE(6) EVT_LN_CASE(7)
@@ -167,10 +173,11 @@ int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const
   EVT_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
   EVT_CHECK_ARG(rows > 0 && D > 0, "layernorm: rows and D must be positive");
   EVT_CHECK_ARG(x_stride >= D && y_stride >= D, "layernorm: stride smaller than D");
-  EVT_CHECK_ARG(y_dtype == EVT_BF16 || y_dtype == EVT_F32, "layernorm: y dtype must be bf16 or f32");
+  EVT_CHECK_ARG(y_dtype == EVT_BF16 || y_dtype == EVT_F32 || y_dtype == EVT_TF32, "layernorm: y dtype must be bf16, f32 or tf32");
   EVT_CHECK_ARG(eps >= 0.f, "layernorm: negative eps");
-  if (y_dtype == EVT_BF16) return launch_rows<true>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
-  return launch_rows<false>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
+  if (y_dtype == EVT_BF16) return launch_rows<EVT_BF16>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
+  if (y_dtype == EVT_TF32) return launch_rows<EVT_TF32>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
+  return launch_rows<EVT_F32>(x, x_stride, gamma, beta, y, y_stride, y_copy, rows, D, eps, st);
 }
 
 }  // namespace evt

@@ -16,34 +16,40 @@
 #include <vector>
 
 #include "ops.h"
+#include "ptx.cuh"
 
 namespace evt {
 namespace {
 
-__global__ void __launch_bounds__(256) convert_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                          long long rows, int cols, int ld) {
+__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_as(float* p, float v) { *p = ptx::round_tf32(v); }  // f32 storage == tf32 operand
+
+template <typename T>
+__global__ void __launch_bounds__(256) convert_pad_kernel(const float* __restrict__ src, T* __restrict__ dst, long long rows,
+                                                          int cols, int ld) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= rows * ld) return;
   const int c = static_cast<int>(t % ld);
   const long long r = t / ld;
-  dst[t] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+  store_as(dst + t, c < cols ? src[r * cols + c] : 0.f);
 }
 
 // bf16 rows gathered with a stride from an f32 matrix (cls rows for a head without final LN)
+template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_cast_kernel(const float* __restrict__ x, long long x_stride,
-                                                               __nv_bfloat16* __restrict__ y, long long rows, int D) {
+                                                               T* __restrict__ y, long long rows, int D) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= rows * D) return;
   const int c = static_cast<int>(t % D);
   const long long r = t / D;
-  y[t] = __float2bfloat16_rn(x[r * x_stride + c]);
+  store_as(y + t, x[r * x_stride + c]);
 }
 
-inline int pad8(int v) { return (v + 7) / 8 * 8; }
+inline int padn(int v, int n) { return (v + n - 1) / n * n; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct LayerW {
-  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  uint8_t *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // bf16 or f32 (tf32 mode) matrices
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   int a = 0, inter = 0, inter_ld = 0;
@@ -57,15 +63,17 @@ struct evt_model {
   int device = 0;
   bool loaded = false;
   int patches = 0, n_prefix = 0, patch_k = 0;
+  int es = 2;    // bytes per GEMM operand element: 2 (bf16) or 4 (tf32 mode)
+  int pad = 8;   // elements per 16 bytes
   std::vector<evt::LayerW> layers;
-  __nv_bfloat16* w_patch = nullptr;
+  uint8_t* w_patch = nullptr;
   float* b_patch = nullptr;
   float* prefix = nullptr;  // [n_prefix, D]
   float* pos = nullptr;     // [tokens, D]
   float *lnf_g = nullptr, *lnf_b = nullptr;
-  __nv_bfloat16* w_pre = nullptr;
+  uint8_t* w_pre = nullptr;
   float* b_pre = nullptr;
-  __nv_bfloat16* w_cls = nullptr;
+  uint8_t* w_cls = nullptr;
   float* b_cls = nullptr;
   std::vector<void*> allocs;
 };
@@ -75,7 +83,7 @@ namespace {
 
 struct Workspace {
   float* resid;
-  __nv_bfloat16 *xn, *qkv, *ctx, *big, *clsn, *hh;
+  uint8_t *xn, *qkv, *ctx, *big, *clsn, *hh;  // activations in the GEMM operand type (bf16, or f32 in tf32 mode)
   size_t bytes;
 };
 
@@ -86,7 +94,7 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   int amax = 0, imax_ld = 0;
   for (int l = 0; l < s.layers; ++l) {
     amax = std::max(amax, s.heads[l] * s.head_size);
-    imax_ld = std::max(imax_ld, pad8(s.inter[l]));
+    imax_ld = std::max(imax_ld, padn(s.inter[l], m->pad));
   }
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -97,19 +105,20 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   Workspace w;
   const size_t o_resid = take(M * s.hidden * 4);
-  const size_t o_xn = take(M * s.hidden * 2);
-  const size_t o_qkv = take(M * 3 * amax * 2);
-  const size_t o_ctx = take(M * amax * 2);
-  const size_t o_big = take(std::max(M * imax_ld, Mp * static_cast<size_t>(m->patch_k)) * 2);
-  const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * 2);
-  const size_t o_hh = take(static_cast<size_t>(batch) * std::max(pad8(s.head_hidden), 8) * 2);
+  const size_t es = m->es;
+  const size_t o_xn = take(M * s.hidden * es);
+  const size_t o_qkv = take(M * 3 * amax * es);
+  const size_t o_ctx = take(M * amax * es);
+  const size_t o_big = take(std::max(M * imax_ld, Mp * static_cast<size_t>(m->patch_k)) * es);
+  const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * es);
+  const size_t o_hh = take(static_cast<size_t>(batch) * std::max(padn(s.head_hidden, m->pad), 8) * es);
   w.resid = reinterpret_cast<float*>(b + o_resid);
-  w.xn = reinterpret_cast<__nv_bfloat16*>(b + o_xn);
-  w.qkv = reinterpret_cast<__nv_bfloat16*>(b + o_qkv);
-  w.ctx = reinterpret_cast<__nv_bfloat16*>(b + o_ctx);
-  w.big = reinterpret_cast<__nv_bfloat16*>(b + o_big);
-  w.clsn = reinterpret_cast<__nv_bfloat16*>(b + o_cls);
-  w.hh = reinterpret_cast<__nv_bfloat16*>(b + o_hh);
+  w.xn = b + o_xn;
+  w.qkv = b + o_qkv;
+  w.ctx = b + o_ctx;
+  w.big = b + o_big;
+  w.clsn = b + o_cls;
+  w.hh = b + o_hh;
   w.bytes = off;
   return w;
 }
@@ -129,6 +138,7 @@ int validate_spec(const evt_model_spec* s) {
   EVT_CHECK_ARG(s->act == EVT_ACT_GELU_ERF || s->act == EVT_ACT_GELU_TANH, "FFN activation must be erf- or tanh-GELU");
   EVT_CHECK_ARG(s->eps > 0.f, "LayerNorm eps must be positive");
   EVT_CHECK_ARG(s->head_hidden >= 0, "head_hidden must be >= 0");
+  EVT_CHECK_ARG(s->precision == EVT_PREC_BF16 || s->precision == EVT_PREC_TF32, "precision must be bf16 (0) or tf32 (1)");
   if (s->t2t) return fail(EVT_ERR_UNSUPPORTED, "T2T front-end is driven from the op-level API (evt_unfold_nhwc + performer); model-level t2t is not implemented");
   for (int l = 0; l < s->layers; ++l) {
     EVT_CHECK_ARG(s->heads[l] > 0, "every layer must keep at least one head");
@@ -184,23 +194,25 @@ struct Loader {
     *out = reinterpret_cast<float*>(p);
     return EVT_OK;
   }
-  // bf16 [rows, ld] from f32 [rows, cols] into dst (already allocated), zero padded
-  int mat_into(const std::string& name, int64_t rows, int cols, int ld, __nv_bfloat16* dst) {
+  // operand-typed [rows, ld] from f32 [rows, cols] into dst (already allocated), zero padded
+  int mat_into(const std::string& name, int64_t rows, int cols, int ld, uint8_t* dst) {
     const evt_tensor_view* v;
     int rc = need(name, rows * cols, &v);
     if (rc) return rc;
     const long long total = rows * ld;
-    convert_pad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const float*>(v->data), dst, rows, cols, ld);
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    const float* src = reinterpret_cast<const float*>(v->data);
+    if (m->es == 2) convert_pad_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols, ld);
+    else convert_pad_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), rows, cols, ld);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(EVT_ERR_CUDA, std::string("convert_pad: ") + cudaGetErrorString(e));
     return EVT_OK;
   }
-  int mat(const std::string& name, int64_t rows, int cols, int ld, __nv_bfloat16** out) {
+  int mat(const std::string& name, int64_t rows, int cols, int ld, uint8_t** out) {
     void* p;
-    int rc = alloc(static_cast<size_t>(rows) * ld * 2, &p);
+    int rc = alloc(static_cast<size_t>(rows) * ld * m->es, &p);
     if (rc) return rc;
-    *out = reinterpret_cast<__nv_bfloat16*>(p);
+    *out = reinterpret_cast<uint8_t*>(p);
     return mat_into(name, rows, cols, ld, *out);
   }
 };
@@ -222,6 +234,8 @@ extern "C" int evt_model_create(const evt_model_spec* spec, evt_model** out) {
   m->patches = (spec->image / spec->patch) * (spec->image / spec->patch);
   m->n_prefix = spec->tokens - m->patches;
   m->patch_k = 3 * spec->patch * spec->patch;
+  m->es = spec->precision == EVT_PREC_TF32 ? 4 : 2;
+  m->pad = 16 / m->es;
   m->layers.resize(spec->layers);
   *out = m;
   return EVT_OK;
@@ -274,16 +288,16 @@ extern "C" int evt_model_load_weights(evt_model* m, const evt_tensor_view* tenso
     const std::string p = "vit.encoder.layer." + std::to_string(l) + ".";
     w.a = s.heads[l] * s.head_size;
     w.inter = s.inter[l];
-    w.inter_ld = pad8(w.inter);
+    w.inter_ld = padn(w.inter, m->pad);
     void* q;
-    EVT_TRY(L.alloc(static_cast<size_t>(3) * w.a * D * 2, &q));
-    w.wqkv = reinterpret_cast<__nv_bfloat16*>(q);
+    EVT_TRY(L.alloc(static_cast<size_t>(3) * w.a * D * m->es, &q));
+    w.wqkv = reinterpret_cast<uint8_t*>(q);
     EVT_TRY(L.alloc(static_cast<size_t>(3) * w.a * 4, &q));
     w.bqkv = reinterpret_cast<float*>(q);
     const char* names[3] = {"query", "key", "value"};
     for (int t = 0; t < 3; ++t) {
       const std::string base = p + "attention.attention." + names[t];
-      EVT_TRY(L.mat_into(base + ".weight", w.a, D, D, w.wqkv + static_cast<size_t>(t) * w.a * D));
+      EVT_TRY(L.mat_into(base + ".weight", w.a, D, D, w.wqkv + static_cast<size_t>(t) * w.a * D * m->es));
       const evt_tensor_view* v = L.find(base + ".bias");
       if (v) {
         EVT_TRY(L.need(base + ".bias", w.a, &v));
@@ -313,7 +327,7 @@ extern "C" int evt_model_load_weights(evt_model* m, const evt_tensor_view* tenso
     EVT_TRY(L.vec("pre_classifier.bias", s.head_hidden, true, &m->b_pre));
     cls_in = s.head_hidden;
   }
-  EVT_TRY(L.mat("classifier.weight", s.num_labels, cls_in, pad8(cls_in), &m->w_cls));
+  EVT_TRY(L.mat("classifier.weight", s.num_labels, cls_in, padn(cls_in, m->pad), &m->w_cls));
   EVT_TRY(L.vec("classifier.bias", s.num_labels, true, &m->b_cls));
 #undef EVT_TRY
   EVT_CUDA(cudaStreamSynchronize(L.st));
@@ -357,45 +371,54 @@ extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, f
     rc = (expr);      \
     if (rc != EVT_OK) return rc; \
   } while (0)
+  const bool tf32 = s.precision == EVT_PREC_TF32;
+  const int dt = tf32 ? EVT_F32 : EVT_BF16;   // GEMM operand type
+  const int adt = tf32 ? EVT_TF32 : EVT_BF16;  // type activations are WRITTEN in (tf32: f32 storage, rounded to nearest)
   // embeddings
-  EVT_TRY(im2col_launch(pixels, w.big, EVT_BF16, batch, s.image, s.image, s.patch, st));
-  EVT_TRY(gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, EVT_BF16, m->b_patch, m->pos, D, m->patches, m->n_prefix,
+  EVT_TRY(im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
+  EVT_TRY(gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
                       w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
   EVT_TRY(prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
   // encoder
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
     const int a = lw.a;
-    EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, EVT_BF16, D, tf ? w.resid : nullptr, M, D, s.eps, st));
-    EVT_TRY(gemm_launch(w.xn, D, lw.wqkv, D, EVT_BF16, lw.bqkv, nullptr, 0, 0, 0, w.qkv, EVT_BF16, 3 * a, 0, 0, 0, M, 3 * a,
-                        D, EVT_ACT_NONE, st));
-    EVT_TRY(attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
-    EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, EVT_BF16, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
+    EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    EVT_TRY(gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
                         EVT_ACT_NONE, st));
-    EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, EVT_BF16, D, tf ? w.resid : nullptr, M, D, s.eps, st));
-    EVT_TRY(gemm_launch(w.xn, D, lw.w1, D, EVT_BF16, lw.b1, nullptr, 0, 0, 0, w.big, EVT_BF16, lw.inter_ld, 0, 0, 0, M,
-                        lw.inter, D, s.act, st));
-    EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, EVT_BF16, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0,
-                        0, M, D, lw.inter, EVT_ACT_NONE, st));
+    if (tf32)
+      EVT_TRY(attention_tf32_launch(reinterpret_cast<const float*>(w.qkv), 3 * a, reinterpret_cast<float*>(w.ctx), a, nullptr,
+                                    batch, s.tokens, s.heads[l], s.head_size, scale, st));
+    else
+      EVT_TRY(attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
+    EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a, EVT_ACT_NONE,
+                        st));
+    EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    EVT_TRY(gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
+                        st));
+    EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D,
+                        lw.inter, EVT_ACT_NONE, st));
   }
   // head: only the cls row of every image is consumed (SITE/models/vit/modeling_vit.py:641)
   const int64_t tok_stride = static_cast<int64_t>(s.tokens) * D;
   if (s.final_ln) {
-    EVT_TRY(layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, EVT_BF16, D, nullptr, batch, D, s.eps, st));
+    EVT_TRY(layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, adt, D, nullptr, batch, D, s.eps, st));
   } else {
     const long long total = static_cast<long long>(batch) * D;
-    gather_rows_cast_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w.resid, tok_stride, w.clsn, batch, D);
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (tf32) gather_rows_cast_kernel<<<grid, 256, 0, st>>>(w.resid, tok_stride, reinterpret_cast<float*>(w.clsn), batch, D);
+    else gather_rows_cast_kernel<<<grid, 256, 0, st>>>(w.resid, tok_stride, reinterpret_cast<__nv_bfloat16*>(w.clsn), batch, D);
     EVT_LAUNCH_CHECK("gather_rows_cast");
   }
   if (s.head_hidden > 0) {
-    const int hl = pad8(s.head_hidden);
-    EVT_TRY(gemm_launch(w.clsn, D, m->w_pre, D, EVT_BF16, m->b_pre, nullptr, 0, 0, 0, w.hh, EVT_BF16, hl, 0, 0, 0, batch,
-                        s.head_hidden, D, EVT_ACT_GELU_TANH, st));
-    EVT_TRY(gemm_launch(w.hh, hl, m->w_cls, hl, EVT_BF16, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0,
-                        batch, s.num_labels, s.head_hidden, EVT_ACT_NONE, st));
+    const int hl = padn(s.head_hidden, m->pad);
+    EVT_TRY(gemm_launch(w.clsn, D, m->w_pre, D, dt, m->b_pre, nullptr, 0, 0, 0, w.hh, adt, hl, 0, 0, 0, batch, s.head_hidden, D,
+                        EVT_ACT_GELU_TANH, st));
+    EVT_TRY(gemm_launch(w.hh, hl, m->w_cls, hl, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
+                        s.num_labels, s.head_hidden, EVT_ACT_NONE, st));
   } else {
-    EVT_TRY(gemm_launch(w.clsn, D, m->w_cls, D, EVT_BF16, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0,
-                        batch, s.num_labels, D, EVT_ACT_NONE, st));
+    EVT_TRY(gemm_launch(w.clsn, D, m->w_cls, D, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
+                        s.num_labels, D, EVT_ACT_NONE, st));
   }
 #undef EVT_TRY
   return EVT_OK;

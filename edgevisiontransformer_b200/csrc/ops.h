@@ -12,6 +12,9 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
 int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
                      int heads, int head_size, float scale, cudaStream_t stream);
 
+int attention_tf32_launch(const float* qkv, int64_t ldq, float* ctx, int64_t ldc, const float* head_mask, int B, int S,
+                          int heads, int head_size, float scale, cudaStream_t stream);
+
 int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const float* beta, void* y, int y_dtype,
                      int64_t y_stride, float* y_copy, int64_t rows, int D, float eps, cudaStream_t st);
 

@@ -37,6 +37,7 @@ class B200ViTConfig:
     dialect: str = "hf"               # "hf" | "tf"
     final_ln: bool = True
     head_hidden: int = 0
+    precision: str = "bf16"           # "bf16" (2e-2 logit tolerance) | "tf32" (1e-3; f32 activations)
 
     # names the reference's callers read off model.config
     @property
@@ -62,7 +63,8 @@ _ACT = {"gelu": _lib.ACT_GELU_ERF, "gelu_erf": _lib.ACT_GELU_ERF, "gelu_new": _l
 
 
 def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12, hidden_act="gelu", head_size=64,
-                           image_size=224, patch_size=16, dialect="hf", final_ln=None, head_hidden=None) -> B200ViTConfig:
+                           image_size=224, patch_size=16, dialect="hf", final_ln=None, head_hidden=None,
+                           precision="bf16") -> B200ViTConfig:
     D = sd["vit.embeddings.cls_token"].shape[-1]
     L = 0
     while f"vit.encoder.layer.{L}.attention.attention.query.weight" in sd:
@@ -84,7 +86,7 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12,
                          tokens=sd["vit.embeddings.position_embeddings"].shape[-2], image_size=image_size,
                          patch_size=patch_size, num_labels=sd["classifier.weight"].shape[0],
                          layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, dialect=dialect, final_ln=bool(final_ln),
-                         head_hidden=int(head_hidden))
+                         head_hidden=int(head_hidden), precision=precision)
 
 
 class B200ViTForImageClassification(nn.Module):
@@ -121,6 +123,9 @@ class B200ViTForImageClassification(nn.Module):
         spec.final_ln = int(config.final_ln)
         spec.head_hidden = int(config.head_hidden)
         spec.t2t = 0
+        if config.precision not in ("bf16", "tf32"):
+            raise ValueError(f"unsupported precision {config.precision!r}")
+        spec.precision = _lib.PREC_TF32 if config.precision == "tf32" else _lib.PREC_BF16
         with torch.cuda.device(device):
             _lib.check(self._lib.evt_model_create(C.byref(spec), C.byref(self._handle)), "model_create")
             dev_sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in state_dict.items()
@@ -153,7 +158,7 @@ class B200ViTForImageClassification(nn.Module):
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], config: Optional[B200ViTConfig] = None, **kw):
         sd = normalise_keys(sd)
         cfg_kw = {k: kw.pop(k) for k in list(kw) if k in ("layer_norm_eps", "hidden_act", "head_size", "image_size",
-                                                            "patch_size", "dialect", "final_ln", "head_hidden")}
+                                                            "patch_size", "dialect", "final_ln", "head_hidden", "precision")}
         config = config or config_from_state_dict(sd, **cfg_kw)
         return cls(config, sd, **kw)
 
@@ -166,14 +171,14 @@ class B200ViTForImageClassification(nn.Module):
         config = config_from_state_dict(
             sd, layer_norm_eps=getattr(hf_cfg, "layer_norm_eps", 1e-12), hidden_act=getattr(hf_cfg, "hidden_act", "gelu"),
             head_size=hf_cfg.hidden_size // hf_cfg.num_attention_heads, image_size=_first(hf_cfg.image_size),
-            patch_size=_first(hf_cfg.patch_size))
+            patch_size=_first(hf_cfg.patch_size), precision=kw.pop("precision", "bf16"))
         return cls(config, sd, **kw)
 
     @classmethod
     def from_pretrained(cls, model_dir: str, **kw):
         from .checkpoint import load_checkpoint
         sd, cfg_kw = load_checkpoint(model_dir)
-        cfg_kw.update({k: kw.pop(k) for k in list(kw) if k in ("hidden_act", "layer_norm_eps")})
+        cfg_kw.update({k: kw.pop(k) for k in list(kw) if k in ("hidden_act", "layer_norm_eps", "precision")})
         return cls.from_state_dict(sd, **cfg_kw, **kw)
 
     # ------------------------------------------------------------------ nn.Module surface

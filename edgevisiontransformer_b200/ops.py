@@ -126,15 +126,16 @@ def attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_size: int = 64
               head_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv bf16 [B*S, 3*heads*head_size] (q | k | v blocks) -> ctx bf16 [B*S, heads*head_size]."""
     _need_cuda(qkv, head_mask)
-    if qkv.dtype != torch.bfloat16 or qkv.dim() != 2 or qkv.stride(1) != 1:
-        raise ValueError("attention wants a 2-D bf16 qkv matrix")
+    if qkv.dtype not in (torch.bfloat16, torch.float32) or qkv.dim() != 2 or qkv.stride(1) != 1:
+        raise ValueError("attention wants a 2-D bf16 (or f32 for the tf32 mode) qkv matrix")
     if qkv.shape[0] != B * S or qkv.shape[1] < 3 * heads * head_size:
         raise ValueError("attention: qkv shape does not match B, S, heads")
-    ctx = torch.empty((B * S, heads * head_size), dtype=torch.bfloat16, device=qkv.device)
+    ctx = torch.empty((B * S, heads * head_size), dtype=qkv.dtype, device=qkv.device)
     scale = float(head_size ** -0.5 if scale is None else scale)
     lib = _lib.load()
-    _lib.check(lib.evt_attention_fwd(qkv.data_ptr(), qkv.stride(0), ctx.data_ptr(), ctx.stride(0), _ptr(head_mask), B, S,
-                                     heads, head_size, scale, _stream()), "attention")
+    fn = lib.evt_attention_fwd if qkv.dtype == torch.bfloat16 else lib.evt_attention_fwd_tf32
+    _lib.check(fn(qkv.data_ptr(), qkv.stride(0), ctx.data_ptr(), ctx.stride(0), _ptr(head_mask), B, S, heads, head_size,
+                  scale, _stream()), "attention")
     return ctx
 
 

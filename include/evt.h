@@ -37,7 +37,9 @@ enum evt_status {
   EVT_ERR_STATE = -4         /* call order violated (e.g. forward before weights loaded)   */
 };
 
-enum evt_dtype { EVT_F32 = 0, EVT_BF16 = 1 };
+/* EVT_TF32 is f32 storage whose values are rounded (to nearest) to tf32 precision when written: use it for
+ * outputs that feed a tf32 GEMM / attention, whose tensor cores would otherwise truncate. */
+enum evt_dtype { EVT_F32 = 0, EVT_BF16 = 1, EVT_TF32 = 2 };
 
 /* activation fused in the GEMM epilogue.  ERF: HF `hidden_act="gelu"`
  * (SITE/models/vit/modeling_vit.py:291-299); TANH: modeling/torch_layers/activation.py:4-7. */
@@ -105,6 +107,10 @@ int evt_gemm_bias_act_tf32(const float* A, int64_t lda, const float* W, int64_t 
 int evt_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask,
                       int B, int S, int heads, int head_size, float scale, evt_stream stream);
 
+/* tf32 flavour of evt_attention_fwd: qkv and ctx are f32 (leading dims multiples of 4). */
+int evt_attention_fwd_tf32(const float* qkv, int64_t ldq, float* ctx, int64_t ldc, const float* head_mask,
+                           int B, int S, int heads, int head_size, float scale, evt_stream stream);
+
 /* Non-overlapping patch gather: pixels f32 NCHW [B,3,H,W] -> bf16 [B*(H/P)*(W/P), 3*P*P] with
  * K order (c, i, j) -- the im2col of Conv2d(3,D,P,P) (SITE/models/vit/modeling_vit.py:151-167). */
 int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream);
@@ -128,6 +134,11 @@ typedef struct evt_model evt_model;
 
 #define EVT_MAX_LAYERS 64
 
+/* arithmetic mode of the whole forward.  BF16: bf16 GEMM / attention operands, f32 accumulate, f32 residual
+ * stream (logits within 2e-2 of the f32 reference).  TF32: f32 activations and weights read as tf32 by the
+ * tensor cores (logits within 1e-3). */
+enum evt_precision { EVT_PREC_BF16 = 0, EVT_PREC_TF32 = 1 };
+
 enum evt_dialect {
   EVT_DIALECT_HF = 0,   /* HF ViT/DeiT: pre-LN, qkv bias, final LN + Linear head            */
   EVT_DIALECT_TF = 1    /* modeling/models/vit.py: skip carries LN(x), no qkv bias, no final
@@ -149,6 +160,7 @@ typedef struct evt_model_spec {
   int final_ln;                /* 1: LayerNorm before the head (HF, T2T); 0: TF-dialect DeiT */
   int head_hidden;             /* 0: single Linear head; >0: Dense(head_hidden, gelu)->Dense */
   int t2t;                     /* 1: T2T front-end (NHWC input) instead of the patch embed   */
+  int precision;               /* evt_precision: 0 bf16 operands, 1 tf32 operands (f32 activations) */
 } evt_model_spec;
 
 typedef struct evt_tensor_view {

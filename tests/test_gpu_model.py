@@ -45,6 +45,21 @@ def test_deit_matches_oracle_and_golden(kind, seed, stress, bs, golden_dir):
     _check(got[:nb], torch.from_numpy(f["logits"]))       # committed fixture from the HF forward itself
 
 
+def test_tf32_mode_config1(golden_dir):
+    """BASELINE config 1: DeiT-Tiny, seed-0 weights, batch 1, input seed 1 -> max-abs 1e-3 in the tf32 mode."""
+    spec = ViTSpec.deit("tiny")
+    for seed, stress in ((0, False), (3, True)):
+        sd = ovit.state_dict_of(ovit.build_hf_model(spec, seed=seed, stress=stress))
+        x = ovit.synthetic_images(2, seed=1)
+        want = ovit.vit_forward(sd, spec, x)
+        m = _model(sd, precision="tf32")
+        got = m(x.cuda()).logits
+        _check(got, want, tol=1e-3)
+        _check(m(x[:1].cuda()).logits, want[:1], tol=1e-3)
+    f = np.load(os.path.join(golden_dir, "hf_tiny_s3_stress.npz"))
+    _check(got, torch.from_numpy(f["logits"]), tol=1e-3)
+
+
 def test_from_hf_and_module_surface():
     from edgevisiontransformer_b200 import B200ViTForImageClassification
     spec = ViTSpec.deit("tiny")

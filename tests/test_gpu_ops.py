@@ -136,6 +136,16 @@ def test_attention(B, S, heads):
     assert err < 2e-2, f"attention err {err}"
 
 
+@pytest.mark.parametrize("B,S,heads", [(2, 197, 3), (1, 198, 1), (3, 128, 2), (1, 256, 2), (2, 16, 1)])
+def test_attention_tf32(B, S, heads):
+    ops = _ops()
+    qkv = _rand((B * S, 3 * heads * 64), 1, 1.0)
+    ctx = ops.attention(qkv, B, S, heads)
+    ref = _attn_ref(qkv, B, S, heads)
+    err = (ctx - ref).abs().max().item()
+    assert ctx.dtype == torch.float32 and err < 3e-3, f"tf32 attention err {err}"
+
+
 def test_attention_head_mask_and_peaky_scores():
     ops = _ops()
     B, S, heads = 2, 197, 3
