@@ -27,7 +27,7 @@ class ModelSpec(C.Structure):
         ("image", C.c_int), ("patch", C.c_int), ("head_size", C.c_int), ("num_labels", C.c_int),
         ("act", C.c_int), ("eps", C.c_float),
         ("heads", C.c_int * MAX_LAYERS), ("inter", C.c_int * MAX_LAYERS),
-        ("final_ln", C.c_int), ("head_hidden", C.c_int), ("t2t", C.c_int), ("precision", C.c_int),
+        ("final_ln", C.c_int), ("head_hidden", C.c_int), ("t2t", C.c_int), ("precision", C.c_int), ("embed_k", C.c_int),
     ]
 
 
@@ -58,6 +58,10 @@ SIGNATURES = {
     "evt_model_load_weights": (_i, [_p, C.POINTER(TensorView), _i, _p]),
     "evt_model_workspace_bytes": (_i, [_p, _i, C.POINTER(_sz)]),
     "evt_model_forward": (_i, [_p, _p, _i, _p, _p, _sz, _p]),
+    "evt_model_forward_embedded": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
+    "evt_unfold_ln_nhwc": (_i, [_p, _i, _p, _i64, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "evt_performer_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
+    "evt_performer_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "evt_model_launches_per_forward": (_i, [_p]),
     "evt_model_destroy": (_i, [_p]),
 }

@@ -139,7 +139,7 @@ int validate_spec(const evt_model_spec* s) {
   EVT_CHECK_ARG(s->eps > 0.f, "LayerNorm eps must be positive");
   EVT_CHECK_ARG(s->head_hidden >= 0, "head_hidden must be >= 0");
   EVT_CHECK_ARG(s->precision == EVT_PREC_BF16 || s->precision == EVT_PREC_TF32, "precision must be bf16 (0) or tf32 (1)");
-  if (s->t2t) return fail(EVT_ERR_UNSUPPORTED, "T2T front-end is driven from the op-level API (evt_unfold_nhwc + performer); model-level t2t is not implemented");
+  EVT_CHECK_ARG(s->embed_k >= 0 && s->embed_k % 8 == 0, "embed_k must be a non-negative multiple of 8");
   for (int l = 0; l < s->layers; ++l) {
     EVT_CHECK_ARG(s->heads[l] > 0, "every layer must keep at least one head");
     EVT_CHECK_ARG(s->inter[l] > 0, "every layer must keep at least one FFN unit");
@@ -233,7 +233,7 @@ extern "C" int evt_model_create(const evt_model_spec* spec, evt_model** out) {
   cudaGetDevice(&m->device);
   m->patches = (spec->image / spec->patch) * (spec->image / spec->patch);
   m->n_prefix = spec->tokens - m->patches;
-  m->patch_k = 3 * spec->patch * spec->patch;
+  m->patch_k = spec->embed_k > 0 ? spec->embed_k : 3 * spec->patch * spec->patch;
   m->es = spec->precision == EVT_PREC_TF32 ? 4 : 2;
   m->pad = 16 / m->es;
   m->layers.resize(spec->layers);
@@ -348,11 +348,11 @@ extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   return 3 + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
-extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits, void* workspace,
-                                 size_t workspace_bytes, evt_stream stream) {
+static int forward_impl(evt_model* m, const float* pixels, const void* patch_matrix, int64_t patch_ld, int batch,
+                        float* logits, void* workspace, size_t workspace_bytes, evt_stream stream) {
   EVT_CHECK_ARG(m != nullptr, "evt_model_forward: model is null");
   if (!m->loaded) return fail(EVT_ERR_STATE, "evt_model_forward called before evt_model_load_weights");
-  EVT_CHECK_ARG(pixels && logits && workspace, "evt_model_forward: null pointer");
+  EVT_CHECK_ARG((pixels || patch_matrix) && logits && workspace, "evt_model_forward: null pointer");
   EVT_CHECK_ARG(batch > 0 && batch <= 65535, "batch must be in 1..65535");
   const evt_model_spec& s = m->spec;
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
@@ -375,8 +375,17 @@ extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, f
   const int dt = tf32 ? EVT_F32 : EVT_BF16;   // GEMM operand type
   const int adt = tf32 ? EVT_TF32 : EVT_BF16;  // type activations are WRITTEN in (tf32: f32 storage, rounded to nearest)
   // embeddings
-  EVT_TRY(im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
-  EVT_TRY(gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
+  const void* pm = patch_matrix;
+  int64_t pm_ld = patch_ld;
+  if (pm == nullptr) {
+    EVT_CHECK_ARG(s.embed_k == 0, "this model takes a caller-built patch matrix (evt_model_forward_embedded)");
+    EVT_TRY(im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
+    pm = w.big;
+    pm_ld = m->patch_k;
+  } else {
+    EVT_CHECK_ARG(pm_ld >= m->patch_k, "patch matrix leading dimension smaller than the embedding K");
+  }
+  EVT_TRY(gemm_launch(pm, pm_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
                       w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
   EVT_TRY(prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
   // encoder
@@ -422,4 +431,16 @@ extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, f
   }
 #undef EVT_TRY
   return EVT_OK;
+}
+
+extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits, void* workspace,
+                                 size_t workspace_bytes, evt_stream stream) {
+  EVT_CHECK_ARG(pixels != nullptr, "evt_model_forward: pixels is null");
+  return forward_impl(m, pixels, nullptr, 0, batch, logits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int evt_model_forward_embedded(evt_model* m, const void* patch_matrix, int64_t ld, int batch, float* logits,
+                                          void* workspace, size_t workspace_bytes, evt_stream stream) {
+  EVT_CHECK_ARG(patch_matrix != nullptr, "evt_model_forward_embedded: patch_matrix is null");
+  return forward_impl(m, nullptr, patch_matrix, ld, batch, logits, workspace, workspace_bytes, stream);
 }

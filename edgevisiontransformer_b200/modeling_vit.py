@@ -38,6 +38,7 @@ class B200ViTConfig:
     final_ln: bool = True
     head_hidden: int = 0
     precision: str = "bf16"           # "bf16" (2e-2 logit tolerance) | "tf32" (1e-3; f32 activations)
+    embed_k: int = 0                  # >0: caller-built patch matrix with this K (T2T: 576), see forward_embedded
 
     # names the reference's callers read off model.config
     @property
@@ -64,7 +65,7 @@ _ACT = {"gelu": _lib.ACT_GELU_ERF, "gelu_erf": _lib.ACT_GELU_ERF, "gelu_new": _l
 
 def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12, hidden_act="gelu", head_size=64,
                            image_size=224, patch_size=16, dialect="hf", final_ln=None, head_hidden=None,
-                           precision="bf16") -> B200ViTConfig:
+                           precision="bf16", embed_k=0) -> B200ViTConfig:
     D = sd["vit.embeddings.cls_token"].shape[-1]
     L = 0
     while f"vit.encoder.layer.{L}.attention.attention.query.weight" in sd:
@@ -86,7 +87,7 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12,
                          tokens=sd["vit.embeddings.position_embeddings"].shape[-2], image_size=image_size,
                          patch_size=patch_size, num_labels=sd["classifier.weight"].shape[0],
                          layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, dialect=dialect, final_ln=bool(final_ln),
-                         head_hidden=int(head_hidden), precision=precision)
+                         head_hidden=int(head_hidden), precision=precision, embed_k=int(embed_k))
 
 
 class B200ViTForImageClassification(nn.Module):
@@ -123,6 +124,7 @@ class B200ViTForImageClassification(nn.Module):
         spec.final_ln = int(config.final_ln)
         spec.head_hidden = int(config.head_hidden)
         spec.t2t = 0
+        spec.embed_k = int(config.embed_k)
         if config.precision not in ("bf16", "tf32"):
             raise ValueError(f"unsupported precision {config.precision!r}")
         spec.precision = _lib.PREC_TF32 if config.precision == "tf32" else _lib.PREC_BF16
@@ -158,7 +160,7 @@ class B200ViTForImageClassification(nn.Module):
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], config: Optional[B200ViTConfig] = None, **kw):
         sd = normalise_keys(sd)
         cfg_kw = {k: kw.pop(k) for k in list(kw) if k in ("layer_norm_eps", "hidden_act", "head_size", "image_size",
-                                                            "patch_size", "dialect", "final_ln", "head_hidden", "precision")}
+                                                            "patch_size", "dialect", "final_ln", "head_hidden", "precision", "embed_k")}
         config = config or config_from_state_dict(sd, **cfg_kw)
         return cls(config, sd, **kw)
 
@@ -250,6 +252,29 @@ class B200ViTForImageClassification(nn.Module):
             for s in range(0, B, self.max_batch):
                 e = min(B, s + self.max_batch)
                 self._run(x[s:e], logits[s:e])
+        return ImageClassifierOutput(logits=logits)
+
+    @torch.no_grad()
+    def forward_embedded(self, patch_matrix: torch.Tensor) -> ImageClassifierOutput:
+        """Forward from the A operand of the token-embedding GEMM ([B*patches, ld], operand dtype): the entry the T2T
+        front-end uses (its last soft split IS that matrix)."""
+        c = self.config
+        patches = c.tokens - 1 if c.tokens == (c.image_size // c.patch_size) ** 2 + 1 else c.tokens - 2
+        if not patch_matrix.is_cuda or patch_matrix.dim() != 2 or patch_matrix.stride(1) != 1 or patch_matrix.shape[0] % patches:
+            raise ValueError("forward_embedded wants a CUDA [B*patches, ld] matrix")
+        want = torch.float32 if c.precision == "tf32" else torch.bfloat16
+        if patch_matrix.dtype != want:
+            raise ValueError(f"forward_embedded wants {want} for precision {c.precision}")
+        B = patch_matrix.shape[0] // patches
+        logits = torch.empty((B, c.num_labels), dtype=torch.float32, device=patch_matrix.device)
+        with torch.cuda.device(self._device):
+            for s in range(0, B, self.max_batch):
+                e = min(B, s + self.max_batch)
+                ws = self._workspace(e - s)
+                pm = patch_matrix[s * patches:e * patches]
+                _lib.check(self._lib.evt_model_forward_embedded(self._handle, pm.data_ptr(), pm.stride(0), e - s,
+                                                                logits[s:e].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                                torch.cuda.current_stream().cuda_stream), "model_forward_embedded")
         return ImageClassifierOutput(logits=logits)
 
     # ------------------------------------------------------------------ latency path: CUDA graph

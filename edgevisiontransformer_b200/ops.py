@@ -175,6 +175,40 @@ def unfold_nhwc(x: torch.Tensor, k: int, s: int, p: int, ld: Optional[int] = Non
     return out
 
 
+def unfold_ln_nhwc(x: torch.Tensor, k: int, s: int, p: int, gamma: Optional[torch.Tensor] = None,
+                   beta: Optional[torch.Tensor] = None, eps: float = 1e-5, ld: Optional[int] = None) -> torch.Tensor:
+    """tf_Unfold fused with the LayerNorm over each unfolded row (gamma/beta None -> plain unfold)."""
+    _need_cuda(x, gamma, beta)
+    x = x.contiguous()
+    B, H, W, Cc = x.shape
+    oh, ow = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    ld = ld or (k * k * Cc + 7) // 8 * 8
+    out = torch.empty((B * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_unfold_ln_nhwc(x.data_ptr(), _dt(x), out.data_ptr(), ld, _ptr(gamma), _ptr(beta), float(eps), B, H, W,
+                                      Cc, k, s, p, _stream()), "unfold_ln")
+    return out
+
+
+def performer(kqv: torch.Tensor, w: torch.Tensor, B: int, T: int, eps: float = 1e-8):
+    """TokenPerformer.single_attn core: kqv bf16 [B*T, >=192] (k|q|v) -> (yattn bf16 [B*T,64], v f32 [B*T,64])."""
+    _need_cuda(kqv, w)
+    if kqv.dtype != torch.bfloat16 or kqv.dim() != 2 or kqv.shape[0] != B * T or kqv.stride(1) != 1:
+        raise ValueError("performer wants a bf16 [B*T, 192] kqv matrix")
+    if tuple(w.shape) != (32, 64) or w.dtype != torch.float32:
+        raise ValueError("performer: w must be f32 [32, 64]")
+    import ctypes as C
+    lib = _lib.load()
+    n = C.c_size_t()
+    _lib.check(lib.evt_performer_workspace_bytes(B, T, C.byref(n)), "performer_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=kqv.device)
+    yattn = torch.empty((B * T, 64), dtype=torch.bfloat16, device=kqv.device)
+    vout = torch.empty((B * T, 64), dtype=torch.float32, device=kqv.device)
+    _lib.check(lib.evt_performer_fwd(kqv.data_ptr(), kqv.stride(0), w.contiguous().data_ptr(), yattn.data_ptr(),
+                                     vout.data_ptr(), ws.data_ptr(), B, T, 64, 32, float(eps), _stream()), "performer")
+    return yattn, vout
+
+
 def launch_count(reset: bool = False) -> int:
     lib = _lib.load()
     n = int(lib.evt_launch_count())

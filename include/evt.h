@@ -128,6 +128,21 @@ int evt_cast_f32_bf16(const float* x, void* y, int64_t n, evt_stream stream);
 int evt_unfold_nhwc(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C,
                     int k, int s, int p, evt_stream stream);
 
+/* T2T soft split fused with the following LayerNorm (TokenPerformer.norm1, transformer_encoder.py:49,97): like
+ * evt_unfold_nhwc, each output row normalised over its k*k*C elements (gamma/beta f32 [k*k*C]; both NULL = no LN). */
+int evt_unfold_ln_nhwc(const void* x, int x_dtype, void* out, int64_t ldo, const float* gamma, const float* beta,
+                       float eps, int B, int H, int W, int C, int k, int s, int p, evt_stream stream);
+
+/* TokenPerformer.single_attn core (modeling/layers/transformer_encoder.py:67-94) for emb = 64, m = 32:
+ *   kqv   : bf16 [B*T, ld], k | q | v in columns [0,64) [64,128) [128,192)   (output of the kqv Dense)
+ *   w     : f32 [32, 64], already multiplied by sqrt(m) (transformer_encoder.py:65)
+ *   yattn : bf16 [B*T, 64] = (qp kptv^T) / (qp.ksum + eps)
+ *   vout  : f32 [B*T, 64]  = v (the skip input that attn_output's GEMM is then added into)
+ *   workspace : evt_performer_workspace_bytes(B, T) bytes. */
+int evt_performer_workspace_bytes(int B, int T, size_t* out);
+int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace,
+                      int B, int T, int emb, int m, float eps, evt_stream stream);
+
 /* ------------------------------------------------------------------ model level ---------- */
 
 typedef struct evt_model evt_model;
@@ -161,6 +176,8 @@ typedef struct evt_model_spec {
   int head_hidden;             /* 0: single Linear head; >0: Dense(head_hidden, gelu)->Dense */
   int t2t;                     /* 1: T2T front-end (NHWC input) instead of the patch embed   */
   int precision;               /* evt_precision: 0 bf16 operands, 1 tf32 operands (f32 activations) */
+  int embed_k;                 /* 0: 3*patch*patch.  >0: K of the token-embedding GEMM when the caller builds the
+                                  patch matrix itself (T2T: 3*3*64 = 576) and calls evt_model_forward_embedded */
 } evt_model_spec;
 
 typedef struct evt_tensor_view {
@@ -180,6 +197,11 @@ int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* out);
 /* logits[batch, num_labels] (f32) = forward(pixels f32 NCHW [batch,3,image,image]); async on stream. */
 int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits,
                       void* workspace, size_t workspace_bytes, evt_stream stream);
+/* Same forward, starting from the A operand of the token-embedding GEMM instead of pixels: patch_matrix is
+ * [batch*patches, ld] in the operand type of the model's precision (bf16, or f32 for tf32).  Used by the T2T front-end
+ * (tokens-to-token module, modeling/models/t2t_vit.py:63-88), whose last soft split produces exactly that matrix. */
+int evt_model_forward_embedded(evt_model* m, const void* patch_matrix, int64_t ld, int batch, float* logits,
+                               void* workspace, size_t workspace_bytes, evt_stream stream);
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int evt_model_launches_per_forward(const evt_model* m);
 int evt_model_destroy(evt_model* m);

@@ -130,3 +130,26 @@ def test_batch_independence_and_chunking():
     assert torch.equal(a, b)
     perm = torch.randperm(37, device="cuda")
     assert torch.equal(m(x[perm]).logits, a[perm])
+
+
+def test_t2t_front_end_and_model():
+    """T2T-ViT against the torch restatement of modeling/models/t2t_vit.py (parity unpinned by the reference: no TF here)."""
+    from edgevisiontransformer_b200 import ops
+    from edgevisiontransformer_b200.modeling_t2t import B200T2TViT
+    from oracle import t2t as ot2t
+    sd = ot2t.init_t2t_vit(hidden=384, depth=3, num_heads=6, mlp_ratio=3.0, seed=0, stress=True)
+    x = ovit.synthetic_images(2, seed=4, channels_last=True)
+    want_logits, want_tok = ot2t.t2t_vit_forward(sd, x, 3, 6, return_tokens=True)
+    m = B200T2TViT(sd, depth=3, num_heads=6)
+    # soft split + LN alone (bit-level gather, LN in f32)
+    u = ops.unfold_ln_nhwc(x.cuda(), 7, 4, 2)
+    assert torch.equal(u[:, :147].cpu(), ot2t.unfold_nhwc(x, 7, 4, 2).reshape(-1, 147).bfloat16())
+    # tokens entering `project`: compare after the project Dense on the CPU side
+    pm = m.tokens(x.cuda())
+    got_tok = pm[:, :576].float().cpu() @ sd["t2t.project.kernel"] + sd["t2t.project.bias"]
+    err = (got_tok.view(2, 196, 384) - want_tok).abs().max().item()
+    assert err < 5e-2, err
+    r = ovit.compare_logits(m(x.cuda()).logits, want_logits)
+    assert r["max_abs"] <= 3e-2 and r["top1_agree"] == 1.0, r
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 224, 224, device="cuda"))
