@@ -1,0 +1,57 @@
+"""World-size-2 gloo tests (CPU) of the only multi-process logic next to the path: contiguous batch sharding and the
+post-loop counter reduce (deit_pruning/src/utils.py:167-168,221-226).  The forward itself has no collective."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from edgevisiontransformer_b200.eval_loop import reduce_counters, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 4096 + 3
+    lo, hi = shard_range(n, rank, world)
+    # every rank "evaluates" its shard: correct = number of even indices, loss = mean index
+    idx = torch.arange(lo, hi)
+    res = {"eval_accuracy": float((idx % 2 == 0).float().mean()), "eval_loss": float(idx.float().mean()), "inference_time": 1.0 + rank}
+    out = reduce_counters(dict(res), "cpu")
+    q.put((rank, lo, hi, res, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, res0, out0), (r1, lo1, hi1, res1, out1) = got
+    assert (lo0, hi0, lo1, hi1) == (0, 2050, 2050, 4099)             # contiguous, disjoint, covering
+    for k in res0:                                                    # rank 0 holds sum / world_size
+        assert abs(out0[k] - (res0[k] + res1[k]) / 2) < 1e-9
+
+
+def test_shard_range_edges():
+    assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (9, 10)
+    assert shard_range(2, 3, 4) == (2, 2)                              # more ranks than items: empty shard
+    cover = [shard_range(4096, r, 8) for r in range(8)]
+    assert cover[0] == (0, 512) and cover[-1] == (3584, 4096)
