@@ -44,6 +44,12 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static std::atomic<int> g_pair_mode{[] {
+  const char* e = getenv("EVT_GEMM_PAIR");
+  return e == nullptr ? -1 : atoi(e);
+}()};
+int gemm_pair_mode() { return g_pair_mode.load(std::memory_order_relaxed); }
+
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode();
@@ -74,6 +80,7 @@ const char* evt_last_error(void) { return evt::g_last_error.c_str(); }
 int evt_version(void) { return EVT_VERSION; }
 int64_t evt_launch_count(void) { return evt::g_launches; }
 void evt_launch_count_reset(void) { evt::g_launches = 0; }
+void evt_gemm_set_pair_mode(int mode) { evt::g_pair_mode.store(mode < 0 ? -1 : (mode != 0), std::memory_order_relaxed); }
 
 int evt_device_check(void) {
   int dev = 0;

@@ -37,6 +37,7 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();
+int gemm_pair_mode();  // -1 auto, 0 never, 1 whenever applicable (evt_gemm_set_pair_mode / EVT_GEMM_PAIR)
 
 // 2-D row-major tensor map: `rows` x `cols` elements of `elem_bytes`, leading dimension ld (elements),
 // box = box_rows x box_cols, 128-byte swizzle (box_cols * elem_bytes must be 128).

@@ -1,0 +1,245 @@
+// CTA-pair flavour of the tcgen05 GEMM (bf16 operands, TMA epilogue): two CTAs on the two SMs of one TPC form a
+// cluster and compute a 256 x BN output tile with tcgen05.mma.cta_group::2.
+//
+//   CTA r of the pair   loads its own 128 rows of A and HALF of the W tile (rows n0 + r*BN/2 ..) -- the tensor core
+//                       reads the other half out of the peer's shared memory, so every W byte crosses L2->SM once
+//                       per pair and each SM's shared memory serves 8 KB instead of 12 KB per K=16 MMA step;
+//   leader (rank 0)     warp 9 issues the MMAs (M = 256: accumulator rows 0..127 land in its own TMEM, rows 128..255
+//                       in the peer's), commits multicast to both CTAs' `empty` / `tfull` barriers;
+//   both CTAs           warp 8 = TMA producer (completion bytes are credited to the LEADER's `full` barrier),
+//                       warps 0-7 = epilogue of their own 128 rows (same code as the 1-CTA kernel), arriving on the
+//                       leader's `tempty` barrier when an accumulator stage has been drained.
+//
+// Used for the large-M encoder GEMMs; small problems stay on the 1-CTA kernel (more, smaller tiles).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "gemm_common.cuh"
+#include "ops.h"
+
+namespace evt {
+namespace {
+
+using namespace gemm_detail;
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int kABytes = BM * kStageRowBytes;
+  static constexpr int kBBytes = (BN / 2) * kStageRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 6 : BN == 192 ? 6 : 8;
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;
+  static constexpr int kStagingBytes = kEpiWarps * kStgBytes;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kBarBytes;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+};
+
+template <int BN, bool OUT_F32, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // The dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up below is identical in
+  // the two CTAs -- required: the MMA and the multicast commits address the peer by shared-memory OFFSET.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kStagingBytes);
+  uint64_t* full = bars;                     // used in the leader only: its producer's arrive + BOTH CTAs' bytes
+  uint64_t* empty = bars + C::kStages;       // per CTA: multicast commit from the leader's MMA thread
+  uint64_t* tfull = bars + 2 * C::kStages;   // per CTA: multicast commit
+  uint64_t* tempty = tfull + 2;              // used in the leader only: 2 x kEpiWarps arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row blocks here
+
+  if (warp == kProducerWarp && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmO);
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 2 * kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kMmaWarp) ptx::tmem_alloc_pair<C::kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // the peer's barriers are initialised and its TMEM is allocated before anyone touches them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          const uint32_t lead_full = ptx::mapa(&full[stage], 0);
+          // The leader expects the bytes of both CTAs; the peer's bytes may land first (the transaction count goes
+          // transiently negative, the phase cannot complete before the leader's arrive) -- no remote arrive needed.
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+          ptx::tma_load_2d_pair(sa, &tmA, lead_full, kb * p.k_step, m0, ptx::kEvictNormal);
+          ptx::tma_load_2d_pair(sb, &tmW, lead_full, kb * p.k_step, n0, ptx::kEvictLast);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc(2 * BM, BN, 1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+          const uint64_t adesc = ptx::smem_desc_sw128(sa);
+          const uint64_t bdesc = ptx::smem_desc_sw128(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per stage row
+            ptx::mma_f16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit_pair(&empty[stage], 3);  // frees the slot in BOTH CTAs once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::mma_commit_pair(&tfull[as], 3);  // accumulator complete (both halves)
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0..7 (both CTAs, own 128 rows)
+    const int quad = warp & 3;
+    const int grp = warp >> 2;
+    uint8_t* stg = staging + warp * kStgBytes;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quad * 32;
+      const int nt0 = (tile % p.tiles_n) * BN;
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      epilogue_tile<BN, false, OUT_F32, ACT, true>(p, &tmO, stg, grp, lane, m0, nt0, t_row);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(&tempty[as], 0));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+
+  // Neither CTA may leave while the other can still reach into its shared memory / TMEM or signal its barriers.
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool OUT_F32, int ACT>
+int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, GemmParams p, cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  auto kern = gemm_pair_kernel<BN, OUT_F32, ACT>;
+  static int configured_dev = -1;
+  static int max_pairs = 0;
+  int dev = 0;
+  EVT_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    EVT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    int n = 0;
+    EVT_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n <= 0) return fail(EVT_ERR_CUDA, "gemm: no CTA pair of this configuration fits on the device");
+    max_pairs = n;
+    if (getenv("EVT_DEBUG")) fprintf(stderr, "evt: gemm_pair_kernel<%d> max active clusters %d, smem %d\n", BN, n, C::kSmemBytes);
+    configured_dev = dev;
+  }
+  CUtensorMap tmW;
+  int rc = make_tmap_2d(&tmW, W, 2, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.K), static_cast<uint64_t>(ldw), BN / 2,
+                        p.k_step);
+  if (rc != EVT_OK) return rc;
+  p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  kern<<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  EVT_LAUNCH_CHECK("gemm_pair_kernel");
+  return EVT_OK;
+}
+
+template <int BN>
+int dispatch_pair(const void* W, int64_t ldw, const CUtensorMap& a, const CUtensorMap& o, const GemmParams& p, bool out_f32,
+                  int act, cudaStream_t s) {
+  if (out_f32) {
+    switch (act) {
+      case EVT_ACT_NONE: return launch_pair<BN, true, EVT_ACT_NONE>(W, ldw, a, o, p, s);
+      case EVT_ACT_GELU_ERF: return launch_pair<BN, true, EVT_ACT_GELU_ERF>(W, ldw, a, o, p, s);
+      default: return launch_pair<BN, true, EVT_ACT_GELU_TANH>(W, ldw, a, o, p, s);
+    }
+  }
+  switch (act) {
+    case EVT_ACT_NONE: return launch_pair<BN, false, EVT_ACT_NONE>(W, ldw, a, o, p, s);
+    case EVT_ACT_GELU_ERF: return launch_pair<BN, false, EVT_ACT_GELU_ERF>(W, ldw, a, o, p, s);
+    default: return launch_pair<BN, false, EVT_ACT_GELU_TANH>(W, ldw, a, o, p, s);
+  }
+}
+
+}  // namespace
+
+namespace gemm_detail {
+
+bool pair_supported(int bn) { return bn == 256 || bn == 192 || bn == 128; }
+
+int gemm_pair_launch(int bn, const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, const GemmParams& p,
+                     bool out_f32, int act, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return dispatch_pair<256>(W, ldw, tmA, tmO, p, out_f32, act, stream);
+    case 192: return dispatch_pair<192>(W, ldw, tmA, tmO, p, out_f32, act, stream);
+    case 128: return dispatch_pair<128>(W, ldw, tmA, tmO, p, out_f32, act, stream);
+  }
+  return fail(EVT_ERR_INVALID, "gemm: no CTA-pair tile configuration");
+}
+
+}  // namespace gemm_detail
+}  // namespace evt

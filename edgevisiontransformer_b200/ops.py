@@ -209,6 +209,11 @@ def performer(kqv: torch.Tensor, w: torch.Tensor, B: int, T: int, eps: float = 1
     return yattn, vout
 
 
+def set_gemm_pair_mode(mode: int) -> None:
+    """-1 automatic, 0 single-CTA GEMM kernel only, 1 CTA-pair (cta_group::2) kernel whenever applicable."""
+    _lib.load().evt_gemm_set_pair_mode(int(mode))
+
+
 def launch_count(reset: bool = False) -> int:
     lib = _lib.load()
     n = int(lib.evt_launch_count())

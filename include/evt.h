@@ -54,6 +54,11 @@ int evt_device_check(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 int64_t evt_launch_count(void);
 void evt_launch_count_reset(void);
+/* GEMM kernel choice: -1 = automatic (CTA-pair kernel, tcgen05 cta_group::2, for problems with at least one
+ * 256-row tile per SM), 0 = always the single-CTA kernel, 1 = the CTA-pair kernel whenever it is applicable.
+ * Results are identical either way (same K order, same epilogue); the switch exists for tests and tuning.
+ * Initial value: environment variable EVT_GEMM_PAIR if set, else -1. */
+void evt_gemm_set_pair_mode(int mode);
 
 /* ------------------------------------------------------------------ op level ------------- */
 

@@ -90,6 +90,49 @@ def test_gemm_bias(M, N, K):
     assert errb < 1e-2 * max(1.0, ref.abs().max().item()), f"bf16-out err {errb}"
 
 
+PAIR_SHAPES = [
+    # (M, N, K): exercise the CTA-pair (cta_group::2) kernel -- 256-row tiles with an M tail inside the leader's half,
+    # inside the peer's half, N tiles of 256 / 192 / 128 incl. N tails, K tails, several tiles per pair (pipeline wrap).
+    (256 * 3 + 57, 768, 192), (256 * 2 + 128 + 31, 2304, 768), (197 * 40, 3072, 768), (197 * 40, 768, 3072),
+    (1000, 576, 192), (1000, 384, 384), (777, 230, 192), (777, 192, 230), (130, 128, 64), (256 * 80, 256, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_pair_kernel_matches_single_cta(M, N, K):
+    """The CTA-pair kernel must reproduce the single-CTA kernel bit for bit (same K order, same epilogue) and both
+    must match the fp32 reference."""
+    ops = _ops()
+    ld = (K + 7) // 8 * 8
+    a = torch.zeros((M, ld), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((N, ld), dtype=torch.bfloat16, device="cuda")
+    a[:, :K] = _rand((M, K), 11).bfloat16()
+    w[:, :K] = _rand((N, K), 12, 0.05).bfloat16()
+    bias = _rand((N,), 13, 0.1)
+    res0 = _rand((M, N), 14)
+    ref = a[:, :K].float() @ w[:, :K].float().t() + bias
+    outs = {}
+    try:
+        for mode in (0, 1):
+            ops.set_gemm_pair_mode(mode)
+            ldo = (N + 7) // 8 * 8
+            ob = torch.zeros((M, ldo), dtype=torch.bfloat16, device="cuda")
+            ops.linear(a, w, bias, act="gelu_erf", out=ob, out_dtype=torch.bfloat16, k=K, n=N)
+            of = None
+            if N % 4 == 0:
+                of = res0.clone()
+                ops.linear(a, w, bias, residual=of, out=of, out_dtype=torch.float32, k=K)
+            outs[mode] = (ob, of)
+    finally:
+        ops.set_gemm_pair_mode(-1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert (outs[1][0][:, :N].float() - ovit.gelu_erf(ref)).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    if outs[0][1] is not None:
+        assert torch.equal(outs[0][1], outs[1][1])
+        assert (outs[1][1] - (ref + res0)).abs().max().item() < 2e-3 * max(1.0, math.sqrt(K) * 0.05)
+
+
 @pytest.mark.parametrize("act", ["gelu_erf", "gelu_tanh"])
 def test_gemm_gelu_and_residual(act):
     ops = _ops()

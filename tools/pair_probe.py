@@ -1,0 +1,19 @@
+"""Times the FC1-shaped GEMM with the single-CTA and the CTA-pair kernel (development tool)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from edgevisiontransformer_b200 import ops
+from tools.gemm_bench import timeit
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 100864
+for (N, K, act, odt, res) in [(3072, 768, "gelu_erf", torch.bfloat16, False), (2304, 768, None, torch.bfloat16, False),
+                              (768, 3072, None, torch.float32, True), (768, 768, None, torch.float32, True)]:
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    b = torch.randn(N, device="cuda") * 0.1
+    out = torch.zeros(M, N, device="cuda", dtype=odt)
+    for mode in (0, 1):
+        ops.set_gemm_pair_mode(mode)
+        ms = timeit(lambda: ops.linear(a, w, b, act=act, residual=out if res else None, out=out, out_dtype=odt))
+        print(f"M={M} N={N} K={K} act={act} pair={mode}: {ms:.3f} ms {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+ops.set_gemm_pair_mode(-1)
