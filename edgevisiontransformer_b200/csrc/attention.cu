@@ -1,17 +1,21 @@
 // Fused short-sequence attention for sm_100a: softmax(Q K^T * scale) V with all keys of one head
-// resident on chip (S <= 256 tokens, head size 64).  One CTA per (query tile of 128 rows, head, image):
+// resident on chip (S <= 256 tokens, head size 64).  Persistent, warp-specialised, one CTA per SM:
 //
-//   warp 4 (one thread)  TMA-loads Q [128x64], K [SKx64], V [SKx64] (bf16, 128B swizzle) straight out of the
-//                        packed QKV activation matrix, issues S = Q K^T (tcgen05.mma, M=128, N=SK, 4 x K=16)
-//                        into TMEM, later O = P V (A operand = P read from TMEM, B = V as an MN-major smem
-//                        operand, SK/16 MMAs) -- no transposes anywhere, no score tensor in HBM.
-//   warps 0-3            one thread per query row (TMEM lane): row max, exp2, bf16 P written back over the
-//                        consumed S columns (tcgen05.st), row sum; then O * 1/sum -> bf16 context.
+//   work item          (image b, head h, query tile mt of 128 rows); a CTA walks (b, h) pairs blockIdx.x, +gridDim.x, ..
+//                      and the query tiles of each pair, so the K/V re-read of the second tile hits L2.
+//   warp 8 (1 thread)  TMA producer: Q [128x64], K [SKx64], V [SKx64] (bf16, 128B swizzle) straight out of the packed
+//                      QKV activation matrix into a ring of 2-4 shared-memory stages -- loads run items ahead.
+//   warp 9 (1 thread)  MMA issuer: S = Q K^T (tcgen05.mma M=128, N=SK, 4 x K=16) into one of two TMEM slots, later
+//                      O = P V (A operand = P read from TMEM, B = V as an MN-major smem operand, SK/16 MMAs) -- no
+//                      transposes anywhere, no score tensor in HBM.  QK of item j is issued before PV of item j-1.
+//   warps 0-3 / 4-7    softmax group 0 / 1, one per TMEM slot (items alternate between the slots, so one group's
+//                      exponentials overlap the other's MMAs, O read-out and stores).  One thread per query row:
+//                      row max (FMNMX3), exp2 on packed f32x2 pairs, bf16 P written back over the consumed S columns
+//                      (tcgen05.st), row sum; then O * 1/sum -> bf16 context.
 //
 // SK = S rounded up to 16; key columns >= S are masked to probability 0, so the extra K/V rows the TMA box
 // picks up (next image's tokens, or zero fill past the end of the matrix) never contribute.
-// TMEM: 256 columns per CTA (S at [0,SK), P overlaid at [0,SK/2), O overlaid at [128,192)), two CTAs per SM
-// so one CTA's softmax overlaps the other's loads and MMAs.
+// TMEM: 2 slots x 256 columns (S at [0,SK), P overlaid at [0,SK/2), O overlaid at [128,192)).
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -23,15 +27,22 @@ namespace {
 
 constexpr int kHD = 64;
 constexpr int kQRows = 128;
-constexpr int kAttnThreads = 160;
-constexpr int kTmemCols = 256;
+constexpr int kAttnThreads = 160;   // tf32 kernel below
+constexpr int kSoftmaxWarps = 8;
+constexpr int kProdWarp = 8;
+constexpr int kIssueWarp = 9;
+constexpr int kThreadsP = 32 * (kSoftmaxWarps + 2);
+constexpr int kSlotCols = 256;
 constexpr int kOCol = 128;
+constexpr int kMaxStages = 4;
 
 struct AttnParams {
   __nv_bfloat16* ctx;
   const float* head_mask;
   long long ldc;
-  int S, SK, heads;
+  int S, SK, heads, B;
+  int n_mt;      // query tiles per (image, head)
+  int n_stages;  // shared-memory ring depth
   float scale_log2e;
 };
 
@@ -40,169 +51,312 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+// Item j of this CTA -> (image, head, query tile).  Consecutive items share (b, h); the tile order flips on every
+// other pair so that each softmax group (slot = j & 1) sees full and ragged query tiles alternately.
+struct Item {
+  int b, h, mt;
+};
+__device__ __forceinline__ Item item_of(const AttnParams& p, int j) {
+  const int ql = j / p.n_mt;
+  const int s = j - ql * p.n_mt;
+  const int pair = blockIdx.x + ql * gridDim.x;
+  Item it;
+  it.b = pair / p.heads;
+  it.h = pair - it.b * p.heads;
+  it.mt = p.n_mt == 2 ? (s ^ (ql & 1)) : s;
+  return it;
+}
+
+// Row max over W score columns held in r (columns >= nvalid ignored when MASKED).
+template <int W, bool MASKED>
+__device__ __forceinline__ void chunk_max(const uint32_t (&r)[W], int nvalid, float (&m)[4]) {
+  if (!MASKED) {
+#pragma unroll
+    for (int j = 0; j < W; j += 8) {
+      m[0] = max3(m[0], __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+      m[1] = max3(m[1], __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      m[2] = max3(m[2], __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+      m[3] = max3(m[3], __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (j < nvalid) m[j & 3] = fmaxf(m[j & 3], __uint_as_float(r[j]));
+  }
+}
+// p = 2^(s*scale - m*scale) for W columns -> bf16 pairs in pk[W/2], f32 sums accumulated in sum2[2] (packed pairs).
+template <int W, bool MASKED>
+__device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int nvalid, uint64_t scale2, uint64_t negm2,
+                                          uint64_t (&sum2)[2], uint32_t (&pk)[W / 2]) {
+#pragma unroll
+  for (int j = 0; j < W; j += 2) {
+    float t0, t1;
+    upk2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+    float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+    if (MASKED) {
+      if (j >= nvalid) p0 = 0.f;
+      if (j + 1 >= nvalid) p1 = 0.f;
+    }
+    sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pk2(p0, p1));
+    __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+    pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsP, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_bytes = p.SK * 128;
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kQRows * 128;
-  uint8_t* sV = sK + kv_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_bytes);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  const int stage_bytes = kQRows * 128 + 2 * kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * stage_bytes);
+  uint64_t* full = bars;                      // [kMaxStages] producer -> issuer
+  uint64_t* empty = bars + kMaxStages;        // [kMaxStages] issuer (commit) -> producer
+  uint64_t* s_ready = bars + 2 * kMaxStages;  // [2] issuer (commit) -> softmax group
+  uint64_t* p_ready = s_ready + 2;            // [2] softmax group (4 warps) -> issuer
+  uint64_t* o_ready = p_ready + 2;            // [2] issuer (commit) -> softmax group
+  uint64_t* slot_free = o_ready + 2;          // [2] softmax group (4 warps) -> issuer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int a = p.heads * kHD;
+  const int total_pairs = p.B * p.heads;
+  const int my_pairs = (total_pairs - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_items = my_pairs * p.n_mt;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      ptx::prefetch_tmap(&tmQ);
-      ptx::prefetch_tmap(&tmKV);
-      ptx::mbar_init(bar_load, 1);
-      ptx::mbar_init(bar_s, 1);
-      ptx::mbar_init(bar_p, 128);
-      ptx::mbar_init(bar_o, 1);
-      ptx::fence_mbar_init();
+  if (warp == kProdWarp && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
+    for (int s = 0; s < kMaxStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
     }
-    __syncwarp();
-    ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_ready[s], 1);
+      ptx::mbar_init(&p_ready[s], 4);
+      ptx::mbar_init(&o_ready[s], 1);
+      ptx::mbar_init(&slot_free[s], 4);
+    }
+    ptx::fence_mbar_init();
   }
+  if (warp == kIssueWarp) ptx::tmem_alloc<512>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int row0 = b * p.S;
-      ptx::mbar_arrive_expect_tx(bar_load, kQRows * 128 + 2 * kv_bytes);
-      ptx::tma_load_2d(sQ, &tmQ, bar_load, h * kHD, row0 + mt * kQRows);
-      ptx::tma_load_2d(sK, &tmKV, bar_load, a + h * kHD, row0);
-      ptx::tma_load_2d(sV, &tmKV, bar_load, 2 * a + h * kHD, row0);
-      ptx::mbar_wait(bar_load, 0);
-      ptx::tc_fence_after();
-      {  // S = Q K^T
-        const uint32_t idesc = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
-        const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
-        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK));
-#pragma unroll
-        for (int k = 0; k < kHD / 16; ++k) ptx::mma_f16_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc, k != 0 ? 1u : 0u);
-        ptx::mma_commit(bar_s);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_items; ++j) {
+        const Item it = item_of(p, j);
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        uint8_t* sQ = smem + st * stage_bytes;
+        uint8_t* sK = sQ + kQRows * 128;
+        uint8_t* sV = sK + kv_bytes;
+        const int row0 = it.b * p.S;
+        ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+        ptx::tma_load_2d(sQ, &tmQ, &full[st], it.h * kHD, row0 + it.mt * kQRows);
+        ptx::tma_load_2d(sK, &tmKV, &full[st], a + it.h * kHD, row0);
+        ptx::tma_load_2d(sV, &tmKV, &full[st], 2 * a + it.h * kHD, row0);
+        if (++st == p.n_stages) {
+          st = 0;
+          ph ^= 1;
+        }
       }
-      ptx::mbar_wait(bar_p, 0);
-      ptx::tc_fence_after();
-      {  // O = P V ; P from TMEM (bf16 pairs, 8 columns per K=16), V MN-major from smem (16 key rows = 2048 B per step)
-        const uint32_t idesc = ptx::make_idesc(kQRows, kHD, 1, 0, 1);
-        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV));
-        const int nk = p.SK / 16;
+    }
+  } else if (warp == kIssueWarp) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
+      const uint32_t idesc_pv = ptx::make_idesc(kQRows, kHD, 1, 0, 1);
+      const int nk = p.SK / 16;
+      auto issue_pv = [&](int jj) {  // O = P V of item jj; P from TMEM (8 columns per K=16), V MN-major (2048 B per step)
+        const int sl = jj & 1;
+        const int st = jj % p.n_stages;
+        ptx::mbar_wait(&p_ready[sl], (jj >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t slot = tmem_base + sl * kSlotCols;
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(smem + st * stage_bytes + kQRows * 128 + kv_bytes));
         for (int k = 0; k < nk; ++k)
-          ptx::mma_f16_ts(tmem_base + kOCol, tmem_base + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc,
-                          k != 0 ? 1u : 0u);
-        ptx::mma_commit(bar_o);
+          ptx::mma_f16_ts(slot + kOCol, slot + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+        ptx::mma_commit(&o_ready[sl]);
+        ptx::mma_commit(&empty[st]);  // Q, K, V of this stage are no longer needed
+      };
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_items; ++j) {
+        const int sl = j & 1;
+        ptx::mbar_wait(&full[st], ph);
+        ptx::mbar_wait(&slot_free[sl], ((j >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        {  // S = Q K^T
+          const uint32_t sq = ptx::smem_u32(smem + st * stage_bytes);
+          const uint64_t qd = ptx::smem_desc_sw128(sq);
+          const uint64_t kd = ptx::smem_desc_sw128(sq + kQRows * 128);
+          const uint32_t slot = tmem_base + sl * kSlotCols;
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) ptx::mma_f16_ss(slot, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+          ptx::mma_commit(&s_ready[sl]);
+        }
+        if (j > 0) issue_pv(j - 1);
+        if (++st == p.n_stages) {
+          st = 0;
+          ph ^= 1;
+        }
       }
+      if (n_items > 0) issue_pv(n_items - 1);
     }
   } else {
-    const int qrow = mt * kQRows + warp * 32 + lane;  // query index within the image
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int nchunk = p.SK / 16;
-    ptx::mbar_wait(bar_s, 0);
-    ptx::tc_fence_after();
-    // Warps whose 32 query rows are all past the sequence end (rows 224..255 of the second tile when S = 197)
-    // skip the softmax arithmetic; their P / O lanes hold garbage that is never stored.
-    const bool warp_live = mt * kQRows + warp * 32 < p.S;
-    float sum = 1.f;
-    if (warp_live) {
-      const int nfull = p.S / 16;  // chunks with no masked key
-      // pass 1: row max over the valid keys
-      float m = -CUDART_INF_F;
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_row + c * 16, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-      }
-      if (nfull < nchunk) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_row + nfull * 16, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nfull * 16 + j < p.S) m = fmaxf(m, __uint_as_float(r[j]));
-      }
-      // pass 2: probabilities (bf16) written over the S columns already consumed; fp32 row sum
-      const float msl = m * p.scale_log2e;
-      float s0 = 0.f, s1 = 0.f;
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_row + c * 16, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl));
-          s0 += p0;
-          s1 += p1;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+    // ------------------------------------------------------------ softmax groups
+    const int grp = warp >> 2;
+    const int quad = warp & 3;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * kSlotCols;
+    const int n16 = p.SK / 16;                    // 16-column score chunks; only the last one can hold masked keys
+    const int last_valid = p.S - (n16 - 1) * 16;  // valid columns in it (1..16)
+    const uint64_t scale2 = pk2(p.scale_log2e, p.scale_log2e);
+#pragma unroll 1
+    for (int j = grp; j < n_items; j += 2) {
+      const Item it = item_of(p, j);
+      const uint32_t ph = (j >> 1) & 1;
+      const int qrow0 = it.mt * kQRows + quad * 32;
+      const bool warp_live = qrow0 < p.S;  // rows 224..255 of the second tile when S = 197: nothing to do
+      ptx::mbar_wait(&s_ready[grp], ph);
+      ptx::tc_fence_after();
+      float sum = 1.f;
+      if (warp_live) {
+        // Both passes walk the row in 16-column chunks, double-buffered: the next tcgen05.ld is in flight while the
+        // current chunk is reduced / exponentiated.
+        uint32_t ra[16], rb[16];
+        // pass 1: row max
+        float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        {
+          ptx::tmem_ld_x16(t_row, ra);
+          int c = 0;
+#pragma unroll 1
+          for (; c + 2 <= n16 - 1; c += 2) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+            chunk_max<16, false>(ra, 16, m);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
+            chunk_max<16, false>(rb, 16, m);
+          }
+          if (c + 1 < n16) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+            chunk_max<16, false>(ra, 16, m);
+            ptx::tmem_ld_wait();
+            chunk_max<16, true>(rb, last_valid, m);
+          } else {
+            ptx::tmem_ld_wait();
+            chunk_max<16, true>(ra, last_valid, m);
+          }
         }
-        ptx::tmem_st_x8(t_row + c * 8, pk);
-      }
-      if (nfull < nchunk) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_row + nfull * 16, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const int key = nfull * 16 + j;
-          const float p0 = key < p.S ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -msl)) : 0.f;
-          const float p1 = key + 1 < p.S ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -msl)) : 0.f;
-          s0 += p0;
-          s1 += p1;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+        const float nm = -mx * p.scale_log2e;
+        const uint64_t negm2 = pk2(nm, nm);
+        // pass 2: probabilities (bf16) written over the S columns already consumed; fp32 row sum
+        uint64_t sum2[2] = {0ull, 0ull};
+        {
+          uint32_t pk[8];
+          ptx::tmem_ld_x16(t_row, ra);
+          int c = 0;
+#pragma unroll 1
+          for (; c + 2 <= n16 - 1; c += 2) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+            chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
+            ptx::tmem_st_x8(t_row + c * 8, pk);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
+            chunk_exp<16, false>(rb, 16, scale2, negm2, sum2, pk);
+            ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
+          }
+          if (c + 1 < n16) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+            chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
+            ptx::tmem_st_x8(t_row + c * 8, pk);
+            ptx::tmem_ld_wait();
+            chunk_exp<16, true>(rb, last_valid, scale2, negm2, sum2, pk);
+            ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
+          } else {
+            ptx::tmem_ld_wait();
+            chunk_exp<16, true>(ra, last_valid, scale2, negm2, sum2, pk);
+            ptx::tmem_st_x8(t_row + c * 8, pk);
+          }
         }
-        ptx::tmem_st_x8(t_row + nfull * 8, pk);
+        float s0, s1, s2, s3;
+        upk2(sum2[0], s0, s1);
+        upk2(sum2[1], s2, s3);
+        sum = (s0 + s1) + (s2 + s3);
+        ptx::tmem_st_wait();
       }
-      sum = s0 + s1;
-      ptx::tmem_st_wait();
-    }
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(bar_p);
-    // epilogue: O / sum
-    ptx::mbar_wait(bar_o, 0);
-    ptx::tc_fence_after();
-    float inv = 1.0f / sum;
-    if (p.head_mask != nullptr) inv *= p.head_mask[h];
-    const bool valid = qrow < p.S;
-    __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.S + qrow) * p.ldc + h * kHD;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_ready[grp]);
+      // epilogue: O / sum
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));  // sum >= 1 (the max contributes 2^0)
+      if (p.head_mask != nullptr) inv *= p.head_mask[it.h];
+      ptx::mbar_wait(&o_ready[grp], ph);
+      ptx::tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (warp_live) {
+        ptx::tmem_ld_x32(t_row + kOCol, o0);
+        ptx::tmem_ld_x32(t_row + kOCol + 32, o1);
+        ptx::tmem_ld_wait();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&slot_free[grp]);  // the slot can take the next S while we convert and store
+      const int qrow = qrow0 + lane;
+      if (warp_live && qrow < p.S) {
+        __nv_bfloat16* dst = p.ctx + (static_cast<long long>(it.b) * p.S + qrow) * p.ldc + it.h * kHD;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      ptx::tmem_ld_x32(t_row + kOCol + half * 32, r);
-      ptx::tmem_ld_wait();
-      if (valid) {
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-          __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-          __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-          o.x = *reinterpret_cast<uint32_t*>(&t0);
-          o.y = *reinterpret_cast<uint32_t*>(&t1);
-          o.z = *reinterpret_cast<uint32_t*>(&t2);
-          o.w = *reinterpret_cast<uint32_t*>(&t3);
-          *reinterpret_cast<uint4*>(dst + half * 32 + j) = o;
+          for (int jj = 0; jj < 32; jj += 8) {
+            const uint32_t* r = half == 0 ? &o0[jj] : &o1[jj];
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+            o.x = *reinterpret_cast<uint32_t*>(&t0);
+            o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2);
+            o.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(dst + half * 32 + jj) = o;
+          }
         }
       }
     }
@@ -210,9 +364,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kIssueWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    ptx::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -422,17 +576,27 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   p.S = S;
   p.SK = SK;
   p.heads = heads;
+  p.B = B;
+  p.n_mt = (S + kQRows - 1) / kQRows;
   p.scale_log2e = scale * 1.4426950408889634f;
-  const int smem = 1024 + kQRows * 128 + 2 * SK * 128 + 64;
+  const int stage_bytes = kQRows * 128 + 2 * SK * 128;
+  const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
+  const int max_smem = 232448;
+  int n_stages = (max_smem - 1024 - bar_bytes) / stage_bytes;
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (n_stages < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two shared-memory stages");
+  p.n_stages = n_stages;
+  const int smem = 1024 + n_stages * stage_bytes + bar_bytes;
   static int configured_dev = -1;
   int dev = 0;
   EVT_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + kQRows * 128 + 2 * 256 * 128 + 64));
+    EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured_dev = dev;
   }
-  dim3 grid((S + kQRows - 1) / kQRows, heads, B);
-  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmKV, p);
+  const long long pairs = static_cast<long long>(B) * heads;
+  const int grid = pairs < num_sms() ? static_cast<int>(pairs) : num_sms();
+  attention_kernel<<<grid, kThreadsP, smem, stream>>>(tmQ, tmKV, p);
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;
 }
