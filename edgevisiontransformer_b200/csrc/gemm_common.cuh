@@ -91,27 +91,38 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
-// erf-GELU of a pair, in place.  erfc(z) = exp2(z Q(z)) on z = |x|/sqrt(2) in [0, 4] with Q a degree-6 minimax fit
-// of log2(erfc(z))/z (tools/fit_erfc.py: |gelu error| < 7e-7 absolute, < 7e-6 relative; erfc(4) = 1.5e-8 is below
-// f32 resolution of 1, so z is clamped there).  The polynomial is written in a = |x| (powers of 1/sqrt(2) folded
-// into the coefficients).  gelu(x) = x/2 (1 + sign(x)(1 - erfc)) = (x/2 + |x/2|) - |x/2| erfc.
-// Per element: 1 MUFU (ex2), 3.5 packed FMA-class ops, 3 scalar ops -- the A&S 7.1.26 form needs 2 MUFU + 13 scalar.
+// erf-GELU of a pair, in place.  erfc(z) = exp2(z Q(z)) on z = |x|/sqrt(2) in [0, 4] with Q a minimax fit of
+// log2(erfc(z))/z (tools/fit_erfc.py; erfc(4) = 1.5e-8 is below f32 resolution of 1, so z is clamped there).  The
+// polynomial is written in a = |x| (powers of 1/sqrt(2) folded into the coefficients) and the exponent carries an extra
+// -1, so e = erfc/2 and   gelu(x) = x/2 (1 + sign(x)(1 - erfc)) = max(x, 0) - |x| e.
+//   HI (f32 output):  degree 6, |gelu error| < 7e-7 absolute, < 7e-6 relative
+//   !HI (bf16 output): degree 5, < 6e-6 absolute, < 4e-5 relative = 1 % of a bf16 ulp
+// Per element: 1 MUFU (ex2), DEG + 2 FMA-pipe lane operations (packed two per instruction), 2 ALU-pipe min/max, against
+// 2 MUFU + 13 FMA for the textbook A&S 7.1.26 form -- the FMA pipe is what the FC1 epilogue saturates.
+template <bool HI>
 __device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1) {
   constexpr float kAmax = 5.65685424949238f;  // 4 sqrt(2)
   const uint64_t a = pk2(fminf(fabsf(x0), kAmax), fminf(fabsf(x1), kAmax));
-  uint64_t q = fma2(a, pk2(-1.765649017e-06f, -1.765649017e-06f), pk2(6.025074981e-05f, 6.025074981e-05f));
-  q = fma2(q, a, pk2(-9.201008943e-04f, -9.201008943e-04f));
-  q = fma2(q, a, pk2(8.467212319e-03f, 8.467212319e-03f));
-  q = fma2(q, a, pk2(-5.387612060e-02f, -5.387612060e-02f));
-  q = fma2(q, a, pk2(-4.585517347e-01f, -4.585517347e-01f));
-  q = fma2(q, a, pk2(-1.151212096e+00f, -1.151212096e+00f));
+  uint64_t q;
+  if (HI) {
+    q = fma2(a, pk2(-1.765649017e-06f, -1.765649017e-06f), pk2(6.025074981e-05f, 6.025074981e-05f));
+    q = fma2(q, a, pk2(-9.201008943e-04f, -9.201008943e-04f));
+    q = fma2(q, a, pk2(8.467212319e-03f, 8.467212319e-03f));
+    q = fma2(q, a, pk2(-5.387612060e-02f, -5.387612060e-02f));
+    q = fma2(q, a, pk2(-4.585517347e-01f, -4.585517347e-01f));
+    q = fma2(q, a, pk2(-1.151212096e+00f, -1.151212096e+00f));
+  } else {
+    q = fma2(a, pk2(2.554092680e-05f, 2.554092680e-05f), pk2(-6.528479280e-04f, -6.528479280e-04f));
+    q = fma2(q, a, pk2(7.452332415e-03f, 7.452332415e-03f));
+    q = fma2(q, a, pk2(-5.191940814e-02f, -5.191940814e-02f));
+    q = fma2(q, a, pk2(-4.602991641e-01f, -4.602991641e-01f));
+    q = fma2(q, a, pk2(-1.150684714e+00f, -1.150684714e+00f));
+  }
   float t0, t1;
-  upk2(mul2(q, a), t0, t1);
+  upk2(fma2(q, a, pk2(-1.0f, -1.0f)), t0, t1);
   const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-  float h0, h1;
-  upk2(mul2(pk2(x0, x1), pk2(0.5f, 0.5f)), h0, h1);
-  x0 = fmaf(-fabsf(h0), e0, h0 + fabsf(h0));
-  x1 = fmaf(-fabsf(h1), e1, h1 + fabsf(h1));
+  x0 = fmaf(-fabsf(x0), e0, fmaxf(x0, 0.0f));
+  x1 = fmaf(-fabsf(x1), e1, fmaxf(x1, 0.0f));
 }
 // tanh-GELU of a pair: 0.5 x (1 + tanh(u)) == x * sigmoid(2u) ; u = sqrt(2/pi) (x + 0.044715 x^3)
 __device__ __forceinline__ void gelu_tanh_pair(float& x0, float& x1) {
@@ -124,14 +135,14 @@ __device__ __forceinline__ void gelu_tanh_pair(float& x0, float& x1) {
   x0 *= rcp_approx(1.0f + ex2_approx(t0));
   x1 *= rcp_approx(1.0f + ex2_approx(t1));
 }
-template <int ACT, bool EXACT>
+template <int ACT, bool EXACT, bool HI>
 __device__ __forceinline__ void apply_act_pair(float& x0, float& x1) {
   if (ACT == EVT_ACT_GELU_ERF) {
     if (EXACT) {
       x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));
       x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
     } else {
-      gelu_erf_pair(x0, x1);
+      gelu_erf_pair<HI>(x0, x1);
     }
   } else if (ACT == EVT_ACT_GELU_TANH) {
     if (EXACT) {
@@ -143,7 +154,7 @@ __device__ __forceinline__ void apply_act_pair(float& x0, float& x1) {
   }
 }
 // v[j] = act(v[j] + bias[n0 + j]) for the CH columns of one chunk (columns >= N are don't-care).
-template <int CH, int ACT, bool EXACT>
+template <int CH, int ACT, bool EXACT, bool HI>
 __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict__ bias, int n0, int N, bool full) {
   if (bias != nullptr) {
     if (full) {
@@ -162,7 +173,7 @@ __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict
   }
   if (ACT != EVT_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < CH; j += 2) apply_act_pair<ACT, EXACT>(v[j], v[j + 1]);
+    for (int j = 0; j < CH; j += 2) apply_act_pair<ACT, EXACT, HI>(v[j], v[j + 1]);
   }
 }
 
@@ -229,7 +240,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
           if (c + 2 < NCH && n0 + 2 * CH < p.N) load_res(n0 + 2 * CH);
         }
       }
-      bias_act<CH, ACT, TF32>(v, p.bias, n0, p.N, full);
+      bias_act<CH, ACT, TF32, OUT_F32>(v, p.bias, n0, p.N, full);
       if constexpr (OUT_F32) {
         if (p.round_tf32) {
 #pragma unroll

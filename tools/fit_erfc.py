@@ -1,4 +1,5 @@
-"""Derives the degree-6 polynomial used by the bf16 erf-GELU epilogue (csrc/gemm.cu: gelu_erf_pair).
+"""Derives the polynomials used by the erf-GELU epilogue (csrc/gemm_common.cuh: gelu_erf_pair; degree 6 for f32
+output, degree 5 for bf16 output).
 
 erfc(a / sqrt 2) = 2^(a Q(a)) on a in [0, 4 sqrt 2]; Q is a minimax fit (Lawson iteration) of log2(erfc(a/sqrt2))/a
 in the log domain, so erfc keeps uniform RELATIVE accuracy (the negative tail of GELU is x/2 * erfc).
@@ -37,18 +38,18 @@ def gelu_f32(x, q):
     acc = np.full_like(a, q[-1])
     for c in q[-2::-1]:
         acc = acc * a + c
-    e = np.exp2((acc * a).astype(np.float32)).astype(np.float32)
-    h = np.float32(0.5) * x
-    return (h + np.abs(h)) - np.abs(h) * e
+    e = np.exp2((acc * a - np.float32(1.0)).astype(np.float32)).astype(np.float32)   # erfc / 2
+    return np.maximum(x, np.float32(0.0)) - np.abs(x) * e
 
 
 if __name__ == "__main__":
-    q, log_err = fit()
     x = np.linspace(-12, 12, 2_000_001)
     ref = 0.5 * x * (1.0 + special.erf(x / np.sqrt(2.0)))
-    got = gelu_f32(x, q).astype(np.float64)
-    err = np.abs(got - ref)
-    rel = err / np.maximum(np.abs(ref), 1e-30)
-    print("coefficients (a^6 .. a^0):", ", ".join(f"{v:.9e}f" for v in q[::-1]))
-    print(f"max |log2 erfc| error {log_err:.3e}; gelu max abs error {err.max():.3e} at x={x[err.argmax()]:.3f}; "
-          f"max relative error for |x|<5: {rel[np.abs(x) < 5].max():.3e}")
+    for deg in (6, 5):
+        q, log_err = fit(deg)
+        got = gelu_f32(x, q).astype(np.float64)
+        err = np.abs(got - ref)
+        rel = err / np.maximum(np.abs(ref), 1e-30)
+        print(f"degree {deg} coefficients (a^{deg} .. a^0):", ", ".join(f"{v:.9e}f" for v in q[::-1]))
+        print(f"  max |log2 erfc| error {log_err:.3e}; gelu max abs error {err.max():.3e} at x={x[err.argmax()]:.3f}; "
+              f"max relative error for |x|<5: {rel[np.abs(x) < 5].max():.3e}")
