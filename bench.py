@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="deit_base", choices=sorted(WORKLOADS))
     ap.add_argument("--global-batch", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=512, help="images per forward call inside a step")
+    ap.add_argument("--chunk", type=int, default=1024, help="images per forward call inside a step")
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -48,6 +48,13 @@ static std::atomic<int> g_pair_mode{[] {
   const char* e = getenv("EVT_GEMM_PAIR");
   return e == nullptr ? -1 : atoi(e);
 }()};
+bool gemm_ln_fusion_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EVT_FUSE_LN");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
 int gemm_pair_mode() { return g_pair_mode.load(std::memory_order_relaxed); }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,

@@ -388,11 +388,19 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   EVT_TRY(gemm_launch(pm, pm_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
                       w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
   EVT_TRY(prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
-  // encoder
+  // encoder.  EXPERIMENTAL (EVT_FUSE_LN=1, off by default): with bf16 operands and the HF dataflow the LayerNorm that
+  // FOLLOWS each residual projection can run inside that GEMM's epilogue (gemm3.cu).  It is bit-identical on the residual
+  // stream but measured SLOWER on B200 (0.42 vs 0.22 ms for out-proj + LN at 100k rows): the second pass over the new
+  // residual does not stay in L2 (DRAM reads 750 MB vs 465 MB expected), so no traffic is saved -- see DESIGN.md.
+  const bool fuse_ln = !tf32 && !tf && gemm_ln_fusion_enabled() && gemm_res_ln_supported(M, D, D) &&
+                       (M + 255) / 256 >= num_sms() / 2;
+  bool xn_ready = false;  // w.xn already holds LN1 of the current layer (written by the previous layer's FC2 epilogue)
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
     const int a = lw.a;
-    EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    if (!xn_ready)
+      EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    xn_ready = false;
     EVT_TRY(gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
                         EVT_ACT_NONE, st));
     if (tf32)
@@ -400,13 +408,24 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
                                     batch, s.tokens, s.heads[l], s.head_size, scale, st));
     else
       EVT_TRY(attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
-    EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a, EVT_ACT_NONE,
-                        st));
-    EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    if (fuse_ln) {
+      EVT_TRY(gemm_res_ln_launch(w.ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
+    } else {
+      EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
+                          EVT_ACT_NONE, st));
+      EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    }
     EVT_TRY(gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
                         st));
-    EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D,
-                        lw.inter, EVT_ACT_NONE, st));
+    if (fuse_ln && l + 1 < s.layers) {
+      const LayerW& nx = m->layers[l + 1];
+      EVT_TRY(gemm_res_ln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, w.xn, D,
+                                 M, D, lw.inter, st));
+      xn_ready = true;
+    } else {
+      EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M,
+                          D, lw.inter, EVT_ACT_NONE, st));
+    }
   }
   // head: only the cls row of every image is consumed (SITE/models/vit/modeling_vit.py:641)
   const int64_t tok_stride = static_cast<int64_t>(s.tokens) * D;

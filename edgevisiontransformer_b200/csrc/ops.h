@@ -9,6 +9,12 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
                 int64_t ldo, int out_group, int out_group_stride, int out_group_off, int64_t M, int N, int K, int act,
                 cudaStream_t stream);
 
+// x <- x + A W^T + bias (f32 residual stream, in place) and xn <- LayerNorm(x) gamma + beta (bf16), one kernel (gemm3.cu)
+bool gemm_res_ln_supported(int64_t M, int N, int K);
+int gemm_res_ln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid, int64_t ldr,
+                       const float* gamma, const float* beta, float eps, void* xn, int64_t ldxn, int64_t M, int N, int K,
+                       cudaStream_t stream);
+
 int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
                      int heads, int head_size, float scale, cudaStream_t stream);
 

@@ -122,6 +122,30 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor,
+                              gamma: torch.Tensor, beta: torch.Tensor, eps: float, k: Optional[int] = None,
+                              xn: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """resid[M,N] += a[M,K] @ w[N,K]^T + bias (f32, in place); returns xn = LayerNorm(resid) * gamma + beta (bf16).
+    One kernel: the LayerNorm runs in the GEMM epilogue (N a multiple of 64, <= 1024)."""
+    _need_cuda(a, w, bias, resid, gamma, beta, xn)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or resid.dtype != torch.float32:
+        raise ValueError("linear_residual_layernorm wants bf16 operands and an f32 residual stream")
+    if a.dim() != 2 or w.dim() != 2 or resid.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1 or resid.stride(1) != 1:
+        raise ValueError("linear_residual_layernorm wants 2-D operands with unit inner stride")
+    M, N = resid.shape
+    K = k if k is not None else a.shape[1]
+    if a.shape[0] != M or w.shape[0] != N or a.shape[1] < K or w.shape[1] < K:
+        raise ValueError("linear_residual_layernorm: shape mismatch")
+    if xn is None:
+        xn = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    lib = _lib.load()
+    rc = lib.evt_gemm_residual_layernorm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), resid.data_ptr(),
+                                         resid.stride(0), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                         float(eps), xn.data_ptr(), xn.stride(0), M, N, K, _stream())
+    _lib.check(rc, "gemm_residual_layernorm")
+    return xn
+
+
 def attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_size: int = 64, scale: Optional[float] = None,
               head_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv bf16 [B*S, 3*heads*head_size] (q | k | v blocks) -> ctx bf16 [B*S, heads*head_size]."""

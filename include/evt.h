@@ -101,6 +101,18 @@ int evt_gemm_bias_act_tf32(const float* A, int64_t lda, const float* W, int64_t 
                            float* out, int64_t ldo, int out_group, int out_group_stride, int out_group_off,
                            int64_t M, int N, int K, int act, evt_stream stream);
 
+/* Residual projection with the following LayerNorm fused into the epilogue (bf16 A and W):
+ *     resid[M,N] <- resid + A[M,K] W[N,K]^T + bias        (f32, in place)
+ *     xn[M,N]    <- LayerNorm(resid) * gamma + beta        (bf16)
+ * = ViTSelfOutput.dense + the skip connection + layernorm_after, and ViTOutput.dense + skip + the next layer's
+ * layernorm_before (SITE/models/vit/modeling_vit.py:265-268, 308-312, 333-340), without re-reading the residual
+ * stream from HBM.  Statistics are fp32 with a centred variance (exact for constant rows with eps = 1e-12).
+ * N must be a multiple of 64 in [64, 1024]; returns EVT_ERR_UNSUPPORTED otherwise (callers fall back to
+ * evt_gemm_bias_act + evt_layernorm_fwd, which compute the same thing). */
+int evt_gemm_residual_layernorm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
+                                void* xn, int64_t ldxn, int64_t M, int N, int K, evt_stream stream);
+
 /* Fused softmax(Q K^T * scale) V for short sequences (S <= 256, head size 64):
  * eager_attention_forward SITE/models/vit/modeling_vit.py:171-196 ==
  * modeling/torch_layers/attention.py:36-45 == modeling/layers/attention.py:30-33.

@@ -133,6 +133,51 @@ def test_gemm_pair_kernel_matches_single_cta(M, N, K):
         assert (outs[1][1] - (ref + res0)).abs().max().item() < 2e-3 * max(1.0, math.sqrt(K) * 0.05)
 
 
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 768, 768), (1000, 384, 384), (777, 192, 768), (256 * 3 + 5, 768, 3072),
+                                   (130, 64, 64), (600, 320, 192), (197 * 40, 768, 230), (256 * 80 + 129, 768, 768)])
+def test_gemm_residual_layernorm_fused(M, N, K):
+    """x += a w^T + b ; xn = LN(x): the fused kernel against fp32 torch, and bit-exact residual against the
+    unfused GEMM (same accumulation, same single f32 add)."""
+    ops = _ops()
+    ld = (K + 7) // 8 * 8
+    a = torch.zeros((M, ld), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((N, ld), dtype=torch.bfloat16, device="cuda")
+    a[:, :K] = _rand((M, K), 21).bfloat16()
+    w[:, :K] = _rand((N, K), 22, 0.05).bfloat16()
+    bias = _rand((N,), 23, 0.1)
+    res0 = _rand((M, N), 24) + 0.5 * _rand((M, 1), 25)       # rows with different means
+    gamma = 1 + _rand((N,), 26, 0.1)
+    beta = _rand((N,), 27, 0.1)
+    eps = 1e-12
+    want_res = res0 + a[:, :K].float() @ w[:, :K].float().t() + bias
+    want_xn = torch.nn.functional.layer_norm(want_res, (N,), gamma, beta, eps)
+    res = res0.clone()
+    xn = ops.linear_residual_layernorm(a, w, bias, res, gamma, beta, eps, k=K)
+    torch.cuda.synchronize()
+    unfused = res0.clone()
+    ops.linear(a, w, bias, residual=unfused, out=unfused, out_dtype=torch.float32, k=K)
+    assert torch.equal(res, unfused)
+    assert (res - want_res).abs().max().item() < 2e-3 * max(1.0, math.sqrt(K) * 0.05)
+    ref_xn = torch.nn.functional.layer_norm(res, (N,), gamma, beta, eps)
+    assert (xn.float() - ref_xn).abs().max().item() < 2e-2          # bf16 output of O(1..4) values
+    assert (xn.float() - ref_xn.bfloat16().float()).abs().mean().item() < 1e-3
+    assert (xn.float() - want_xn).abs().max().item() < 4e-2
+
+
+def test_gemm_residual_layernorm_constant_rows():
+    """eps = 1e-12 and rows that are exactly constant: the centred variance must be exactly 0 -> xn == beta."""
+    ops = _ops()
+    M, N, K = 300, 768, 64
+    a = _rand((M, K), 1).bfloat16()
+    w = torch.zeros((N, K), dtype=torch.bfloat16, device="cuda")
+    res = (_rand((M, 1), 2) * 100).expand(M, N).contiguous()
+    gamma = 1 + _rand((N,), 3, 0.1)
+    beta = _rand((N,), 4, 0.1)
+    xn = ops.linear_residual_layernorm(a, w, None, res, gamma, beta, 1e-12)
+    assert torch.isfinite(xn.float()).all()
+    assert (xn.float() - beta.bfloat16().float()).abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("act", ["gelu_erf", "gelu_tanh"])
 def test_gemm_gelu_and_residual(act):
     ops = _ops()
