@@ -55,6 +55,11 @@ bool gemm_ln_fusion_enabled() {
   }();
   return on;
 }
+static std::atomic<int> g_split_k{[] {
+  const char* e = getenv("EVT_GEMM_SPLIT_K");
+  return e == nullptr ? 1 : (atoi(e) != 0);
+}()};
+bool gemm_split_k_enabled() { return g_split_k.load(std::memory_order_relaxed) != 0; }
 int gemm_pair_mode() { return g_pair_mode.load(std::memory_order_relaxed); }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
@@ -87,6 +92,7 @@ const char* evt_last_error(void) { return evt::g_last_error.c_str(); }
 int evt_version(void) { return EVT_VERSION; }
 int64_t evt_launch_count(void) { return evt::g_launches; }
 void evt_launch_count_reset(void) { evt::g_launches = 0; }
+void evt_gemm_set_split_k(int enable) { evt::g_split_k.store(enable != 0, std::memory_order_relaxed); }
 void evt_gemm_set_pair_mode(int mode) { evt::g_pair_mode.store(mode < 0 ? -1 : (mode != 0), std::memory_order_relaxed); }
 
 int evt_device_check(void) {

@@ -39,7 +39,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // work item = (output tile, K split).  k_splits > 1 only for the TMA reduce-add epilogue, where partial products
+  // of the same tile simply add up in the residual stream (bias comes from split 0).
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
 
   if (warp == kProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -66,10 +68,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / p.k_splits;
+        const int kb0 = (item - tile * p.k_splits) * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int m0 = (tile / p.tiles_n) * BM;
         const int n0 = (tile % p.tiles_n) * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -91,11 +96,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int kb0 = (item % p.k_splits) * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
@@ -103,7 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bdesc = ptx::smem_desc_sw128(sa + C::kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage row
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
             if (TF32) ptx::mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
             else ptx::mma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
           }
@@ -127,13 +134,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stg = staging + warp * kStgBytes;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    GemmParams pe = p;  // epilogue view of the parameters: K splits other than the first add no bias
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / p.k_splits;
+      pe.bias = item - tile * p.k_splits == 0 ? p.bias : nullptr;
       const int m0 = (tile / p.tiles_n) * BM + quad * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      epilogue_tile<BN, TF32, OUT_F32, ACT, TMA_OUT>(p, &tmO, stg, grp, lane, m0, nt0, t_row);
+      epilogue_tile<BN, TF32, OUT_F32, ACT, TMA_OUT>(pe, &tmO, stg, grp, lane, m0, nt0, t_row);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -153,14 +163,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-int choose_bn(int N) {
+// Tile width: the one that pads N least; when that leaves SMs without a tile (small M: the latency path), the
+// narrower width that puts the most CTAs to work.
+int choose_bn(int64_t M, int N) {
   const int cands[4] = {256, 192, 128, 64};
+  const long tiles_m = static_cast<long>((M + BM - 1) / BM);
   int best = 256;
   long best_cost = -1;
   for (int bn : cands) {
     long cost = static_cast<long>((N + bn - 1) / bn) * bn;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
+      best = bn;
+    }
+  }
+  const long sms = num_sms();
+  if (tiles_m * ((N + best - 1) / best) >= sms) return best;
+  long best_busy = -1;
+  for (int bn : cands) {
+    if (bn > best) continue;
+    const long tiles = tiles_m * ((N + bn - 1) / bn);
+    const long busy = tiles < sms ? tiles : sms;
+    if (busy > best_busy) {  // ties keep the wider tile
+      best_busy = busy;
       best = bn;
     }
   }
@@ -180,7 +205,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tm
     configured = true;
     configured_dev = dev;
   }
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
   EVT_LAUNCH_CHECK("gemm_kernel");
@@ -224,7 +249,7 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
   const bool tf32 = in_dtype == EVT_F32;
   const int eb = tf32 ? 4 : 2;
   const int k_step = kStageRowBytes / eb;
-  const int bn = choose_bn(N);
+  const int bn = choose_bn(M, N);
   CUtensorMap tmA, tmW;
   int rc = make_tmap_2d(&tmA, A, eb, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM, k_step);
   if (rc != EVT_OK) return rc;
@@ -267,6 +292,23 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
     rc = make_tmap_2d(&tmO, out, oeb, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo), 32,
                       128 / oeb);
     if (rc != EVT_OK) return rc;
+  }
+  // Split K when a reduce-add epilogue leaves most SMs idle (out-proj / FC2 at batch 1: 6 tiles for 148 SMs).  The
+  // partial products meet in the f32 residual stream through the same TMA reduce-add; their order is not fixed, so
+  // results can differ in the last bit from run to run -- only in this small-M regime; evt_gemm_set_split_k(0) turns it
+  // off, and a forced kernel choice (evt_gemm_set_pair_mode) never splits.
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
+  if (!tf32 && tma_out && residual != nullptr && gemm_pair_mode() < 0 && gemm_split_k_enabled()) {  // not in the accuracy mode
+    const long tiles = static_cast<long>(p.tiles_m) * p.tiles_n;
+    if (tiles * 2 <= num_sms() && p.num_kb >= 4) {
+      int splits = static_cast<int>(num_sms() / tiles);
+      if (splits > p.num_kb / 2) splits = p.num_kb / 2;  // at least two K blocks per split
+      if (splits > 1) {
+        p.kb_per_split = (p.num_kb + splits - 1) / splits;
+        p.k_splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+      }
+    }
   }
   // Large problems run on CTA pairs (cta_group::2, 256-row tiles): half the W traffic per SM.  evt_gemm_set_pair_mode
   // forces the choice (tests exercise both kernels on the same shapes).

@@ -40,6 +40,7 @@ struct GemmParams {
   int res_row_mod, res_row_off;
   int out_group, out_group_stride, out_group_off;
   int tiles_m, tiles_n, num_kb;
+  int k_splits, kb_per_split;  // 1-CTA kernel: K range per work item (split K for reduce-add outputs at small M)
   int k_step;  // elements of K per stage (64 bf16 / 32 tf32)
   int vec_ok;  // out / residual / bias allow 16-byte vector access
   int round_tf32;  // f32 output feeds a tf32 tensor-core op: round to nearest tf32 when written

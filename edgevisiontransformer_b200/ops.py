@@ -238,6 +238,11 @@ def set_gemm_pair_mode(mode: int) -> None:
     _lib.load().evt_gemm_set_pair_mode(int(mode))
 
 
+def set_gemm_split_k(enable: bool) -> None:
+    """Split K over idle SMs for small-batch residual GEMMs (default on: lower latency, last-bit run-to-run variation)."""
+    _lib.load().evt_gemm_set_split_k(1 if enable else 0)
+
+
 def launch_count(reset: bool = False) -> int:
     lib = _lib.load()
     n = int(lib.evt_launch_count())

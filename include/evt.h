@@ -59,6 +59,13 @@ void evt_launch_count_reset(void);
  * Results are identical either way (same K order, same epilogue); the switch exists for tests and tuning.
  * Initial value: environment variable EVT_GEMM_PAIR if set, else -1. */
 void evt_gemm_set_pair_mode(int mode);
+/* Split K across idle SMs for residual (reduce-add) GEMMs whose tile count leaves most of the GPU idle -- the batch-1
+ * latency path (DeiT-Base batch 1: 1.03 -> 0.62 ms).  The partial products meet in the f32 residual stream through TMA
+ * reduce-adds whose order is not fixed, so with splitting on (the default) small-batch bf16 results can differ from run
+ * to run and from one batch size to another by a last-bit f32 difference in the residual stream (which bf16 roundings
+ * downstream turn into logit differences of a few 1e-3, inside the 2e-2 parity budget); 0 turns it off (bit-reproducible,
+ * batch-invariant results).  Large batches and the tf32 accuracy mode never split.  Initial value: environment variable EVT_GEMM_SPLIT_K if set, else 1. */
+void evt_gemm_set_split_k(int enable);
 
 /* ------------------------------------------------------------------ op level ------------- */
 

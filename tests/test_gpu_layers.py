@@ -88,14 +88,19 @@ def test_eval_loop_matches_reference_evaluate_semantics():
     want = ovit.vit_forward(sd, spec, x)
     got = m(x.cuda()).logits.cpu()
     assert ovit.compare_logits(got, want)["max_abs"] <= 2e-2
-    # near-tied random-init logits may legitimately flip under bf16; take labels from images with a clear margin
+    # near-tied random-init logits may legitimately flip under bf16 (and the small-batch kernels split K differently per
+    # batch size): images without a clear margin get a label that is wrong for every implementation
     top2 = want.topk(2, dim=-1).values
     clear = (top2[:, 0] - top2[:, 1]) > 0.05
-    labels = torch.where(clear, want.argmax(-1), got.argmax(-1))
-    labels[::4] = (labels[::4] + 1) % 1000                    # 6 of 23 wrong on purpose
+    labels = torch.where(clear, want.argmax(-1), want.argmin(-1))
+    labels[::4] = (labels[::4] + 1) % 1000                    # every fourth label wrong on purpose
+    wrong = torch.zeros(23, dtype=torch.bool)
+    wrong[::4] = True
+    expected = int((clear & ~wrong).sum())
+    assert expected >= 10
     batches = [(x[i:i + 10], labels[i:i + 10]) for i in range(0, 23, 10)]
     res = evaluate(batches, m, eval_batch_size=10)
-    assert abs(res["eval_accuracy"] - 17.0 / 23.0) < 1e-9
+    assert abs(res["eval_accuracy"] - expected / 23.0) < 1e-9
     ref_loss = np.mean([want[i:i + 10].mean().item() for i in range(0, 23, 10)])
     assert abs(res["eval_loss"] - ref_loss) < 2e-3 and res["inference_time"] > 0
     runner = PipelinedClassifier(m, chunk=8)

@@ -78,7 +78,17 @@ def test_from_hf_and_module_surface():
     with pytest.raises(RuntimeError):
         m(x)                                        # CPU input: no fallback
     g = m.forward_graphed(x.cuda()).logits
-    assert torch.equal(g, out.logits)               # graph replay == eager launch sequence, bit for bit
+    # small batch: split-K reduce-adds land in any order; a last-bit f32 difference can flip bf16 roundings downstream
+    assert (g - out.logits).abs().max().item() < 1e-2
+    from edgevisiontransformer_b200 import ops
+    try:
+        ops.set_gemm_split_k(False)                 # without K splitting: graph replay == eager, bit for bit
+        e = m(pixel_values=x.cuda()).logits
+        m._graphs.clear()
+        assert torch.equal(m.forward_graphed(x.cuda()).logits, e)
+    finally:
+        ops.set_gemm_split_k(True)
+        m._graphs.clear()
     assert m.launches_per_forward() == 3 + 7 * 12 + 2
 
 
@@ -123,13 +133,22 @@ def test_batch_independence_and_chunking():
     """Size-independent property: images are independent units -> any batch split gives identical logits."""
     spec = ViTSpec.deit("tiny")
     sd = ovit.state_dict_of(ovit.build_hf_model(spec, seed=0))
+    from edgevisiontransformer_b200 import ops
     x = ovit.synthetic_images(37, seed=9).cuda()
     m = _model(sd, max_batch=16)
-    a = m(x).logits
-    b = torch.cat([m(x[:5]).logits, m(x[5:]).logits])
-    assert torch.equal(a, b)
-    perm = torch.randperm(37, device="cuda")
-    assert torch.equal(m(x[perm]).logits, a[perm])
+    try:
+        ops.set_gemm_split_k(False)                 # bit-exact invariance holds whenever K is not split
+        a = m(x).logits
+        b = torch.cat([m(x[:5]).logits, m(x[5:]).logits])
+        assert torch.equal(a, b)
+        perm = torch.randperm(37, device="cuda")
+        assert torch.equal(m(x[perm]).logits, a[perm])
+    finally:
+        ops.set_gemm_split_k(True)
+    # default (latency-tuned) small-batch path: same logits up to the f32 summation order of the K splits (which can
+    # flip bf16 roundings downstream: differences of a few 1e-3, inside the 2e-2 parity budget)
+    c = torch.cat([m(x[:5]).logits, m(x[5:]).logits])
+    assert (c - a).abs().max().item() < 1e-2
 
 
 def test_t2t_front_end_and_model():
