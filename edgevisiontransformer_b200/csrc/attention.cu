@@ -169,6 +169,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();  // qkv (previous kernel's output) is complete from here on
 
   if (warp == kProdWarp) {
     // ------------------------------------------------------------ TMA producer
@@ -431,6 +433,8 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();  // qkv (previous kernel's output) is complete from here on
 
   if (warp == 4) {
     if (lane == 0) {
@@ -596,7 +600,7 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   }
   const long long pairs = static_cast<long long>(B) * heads;
   const int grid = pairs < num_sms() ? static_cast<int>(pairs) : num_sms();
-  attention_kernel<<<grid, kThreadsP, smem, stream>>>(tmQ, tmKV, p);
+  EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_rows(static_cast<long long>(B) * S), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;
 }
@@ -638,7 +642,7 @@ int attention_tf32_launch(const float* qkv, int64_t ldq, float* ctx, int64_t ldc
     configured_dev = dev;
   }
   dim3 grid((S + kQRows - 1) / kQRows, heads, B);
-  attention_tf32_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmKV, p);
+  EVT_CUDA(launch_pdl(attention_tf32_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_for_rows(static_cast<long long>(B) * S), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_tf32_kernel");
   return EVT_OK;
 }

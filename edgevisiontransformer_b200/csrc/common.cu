@@ -48,6 +48,13 @@ static std::atomic<int> g_pair_mode{[] {
   const char* e = getenv("EVT_GEMM_PAIR");
   return e == nullptr ? -1 : atoi(e);
 }()};
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EVT_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
 bool gemm_ln_fusion_enabled() {
   static const bool on = [] {
     const char* e = getenv("EVT_FUSE_LN");

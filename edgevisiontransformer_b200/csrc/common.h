@@ -37,6 +37,30 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();
+bool pdl_enabled();  // EVT_PDL=0 launches every kernel with full stream serialization (A/B timing, debugging)
+// Programmatic dependent launch pays on the latency path (batch 1: -12 %, the next kernel's prologue hides behind the
+// previous kernel's tail); at large batch, where every kernel runs for 100+ us, it measured 2 % SLOWER (CTAs parked in
+// griddepcontrol.wait), so only launches over at most this many rows (tokens) ask for it.
+constexpr long long kPdlMaxRows = 32768;
+inline bool pdl_for_rows(long long rows) { return rows <= kPdlMaxRows && pdl_enabled(); }
+
+// Launch with programmatic dependent launch allowed: the kernel must call ptx::grid_dep_wait() before its first
+// global-memory access.  (cudaLaunchKernelEx also honours a compile-time __cluster_dims__.)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool allow,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = allow ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 bool gemm_ln_fusion_enabled();  // EVT_FUSE_LN=1 routes the model runtime through the experimental GEMM+LayerNorm kernel
 bool gemm_split_k_enabled();  // evt_gemm_set_split_k / EVT_GEMM_SPLIT_K
 int gemm_pair_mode();  // -1 auto, 0 never, 1 whenever applicable (evt_gemm_set_pair_mode / EVT_GEMM_PAIR)

@@ -17,6 +17,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // input (b, c, y, x8) so reads are perfectly coalesced; writes are full 16-byte pieces of patch rows.
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ cols,
                                                      int B, int H, int W, int P, long long total) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int w8 = W / 8;
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ p
 // Same gather, f32 output (tf32 mode keeps the patch matrix in fp32).
 __global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict__ px, float* __restrict__ cols, int B,
                                                          int H, int W, int P, long long total) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int w4 = W / 4;
@@ -66,6 +70,8 @@ __global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) prefix_tokens_kernel(const float* __restrict__ prefix,
                                                             const float* __restrict__ pos, float* __restrict__ out,
                                                             int B, int tokens, int n_prefix, int D) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * n_prefix * D;
   if (t >= total) return;
@@ -130,12 +136,12 @@ int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, 
                 "im2col: pointers must be 16-byte aligned");
   if (out_dtype == EVT_BF16) {
     const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
-    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        pixels, reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total);
+    EVT_CUDA(launch_pdl(im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
+                        reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total));
   } else {
     const long long total = static_cast<long long>(B) * 3 * H * (W / 4);
-    im2col_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(pixels, reinterpret_cast<float*>(cols),
-                                                                                  B, H, W, P, total);
+    EVT_CUDA(launch_pdl(im2col_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
+                        reinterpret_cast<float*>(cols), B, H, W, P, total));
   }
   EVT_LAUNCH_CHECK("im2col");
   return EVT_OK;
@@ -146,7 +152,8 @@ int prefix_tokens_launch(const float* prefix, const float* pos, float* out, int 
   EVT_CHECK_ARG(prefix && pos && out, "prefix_tokens: null pointer");
   EVT_CHECK_ARG(B > 0 && tokens > 0 && n_prefix > 0 && n_prefix <= tokens && D > 0, "prefix_tokens: bad sizes");
   const long long total = static_cast<long long>(B) * n_prefix * D;
-  prefix_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prefix, pos, out, B, tokens, n_prefix, D);
+  EVT_CUDA(launch_pdl(prefix_tokens_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * tokens), prefix, pos,
+                      out, B, tokens, n_prefix, D));
   EVT_LAUNCH_CHECK("prefix_tokens");
   return EVT_OK;
 }

@@ -62,6 +62,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();  // the next kernel may begin its own prologue
+  ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer
@@ -207,7 +209,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tm
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  EVT_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, pdl_for_rows(p.M), tmA, tmW, tmO, p));
   EVT_LAUNCH_CHECK("gemm_kernel");
   return EVT_OK;
 }

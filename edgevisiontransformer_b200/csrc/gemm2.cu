@@ -80,6 +80,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::cluster_sync();  // the peer's barriers are initialised and its TMEM is allocated before anyone touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();  // the next kernel may begin its own prologue
+  ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -203,7 +205,7 @@ int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtens
   p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  kern<<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  EVT_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, pdl_for_rows(p.M), tmA, tmW, tmO, p));
   EVT_LAUNCH_CHECK("gemm_pair_kernel");
   return EVT_OK;
 }

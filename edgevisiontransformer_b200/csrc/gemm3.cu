@@ -115,6 +115,8 @@ gemm_pair_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();  // the next kernel may begin its own prologue
+  ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -394,7 +396,7 @@ int launch_ln(const CUtensorMap& tmA, const void* W, int64_t ldw, LnParams p, cu
   if (rc != EVT_OK) return rc;
   p.tiles_n = (p.N + BN - 1) / BN;
   const int pairs = p.row_blocks < max_pairs ? p.row_blocks : max_pairs;
-  kern<<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, p);
+  EVT_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, pdl_for_rows(p.M), tmA, tmW, p));
   EVT_LAUNCH_CHECK("gemm_pair_ln_kernel");
   return EVT_OK;
 }

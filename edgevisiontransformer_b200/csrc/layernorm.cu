@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       void* __restrict__ y, long long y_stride, float* y_copy,
                                                       long long rows, int D, float eps) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        void* __restrict__ y, long long y_stride, float* y_copy,
                                                        long long rows, int D, float eps) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -144,6 +148,8 @@ __global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, lo
                                                               const float* __restrict__ beta, void* __restrict__ y,
                                                               long long y_stride, float* y_copy, long long rows, int D,
                                                               float eps) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -220,7 +226,7 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
     const int nv = (D + 127) / 128;
 #define EVT_LN4_CASE(NVV)                                                                          \
   case NVV:                                                                                        \
-    ln_rows4_kernel<NVV, OUT><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps); \
+    EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     break;
     switch (nv) {
       EVT_LN4_CASE(1) EVT_LN4_CASE(2) EVT_LN4_CASE(3) EVT_LN4_CASE(4) EVT_LN4_CASE(5) EVT_LN4_CASE(6) EVT_LN4_CASE(7)
@@ -228,12 +234,12 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
     }
 #undef EVT_LN4_CASE
   } else if (!fast) {
-    ln_rows_generic_kernel<OUT><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps);
+    EVT_CUDA(launch_pdl(ln_rows_generic_kernel<OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps));
   } else {
     const int nv = (D + 63) / 64;
 #define EVT_LN_CASE(NVV)                                                                          \
   case NVV:                                                                                       \
-    ln_rows_kernel<NVV, OUT><<<grid, wpb * 32, 0, st>>>(x, xs, g, b, y, ys, yc, rows, D, eps); \
+    EVT_CUDA(launch_pdl(ln_rows_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     break;
     switch (nv) {
       EVT_LN_CASE(1) EVT_LN_CASE(2) EVT_LN_CASE(3) EVT_LN_CASE(4) EVT_LN_CASE(5) EVT_LN_CASE(6) EVT_LN_CASE(7)

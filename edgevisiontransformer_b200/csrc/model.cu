@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256) convert_pad_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_cast_kernel(const float* __restrict__ x, long long x_stride,
                                                                T* __restrict__ y, long long rows, int D) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= rows * D) return;
   const int c = static_cast<int>(t % D);
@@ -434,8 +436,13 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   } else {
     const long long total = static_cast<long long>(batch) * D;
     const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-    if (tf32) gather_rows_cast_kernel<<<grid, 256, 0, st>>>(w.resid, tok_stride, reinterpret_cast<float*>(w.clsn), batch, D);
-    else gather_rows_cast_kernel<<<grid, 256, 0, st>>>(w.resid, tok_stride, reinterpret_cast<__nv_bfloat16*>(w.clsn), batch, D);
+    const long long nrows = batch;
+    if (tf32)
+      EVT_CUDA(launch_pdl(gather_rows_cast_kernel<float>, dim3(grid), dim3(256), 0, st, pdl_for_rows(M), static_cast<const float*>(w.resid), tok_stride,
+                          reinterpret_cast<float*>(w.clsn), nrows, D));
+    else
+      EVT_CUDA(launch_pdl(gather_rows_cast_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, pdl_for_rows(M), static_cast<const float*>(w.resid),
+                          tok_stride, reinterpret_cast<__nv_bfloat16*>(w.clsn), nrows, D));
     EVT_LAUNCH_CHECK("gather_rows_cast");
   }
   if (s.head_hidden > 0) {
