@@ -265,9 +265,30 @@ def main():
         ach = flops / (kms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_kernel<256,bf16,gelu_erf> (FC1: M=%d N=%d K=%d)" % (M, inter, d),
                 "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "peak_source": pk["src"] + " (burst: kernel timed alone)", "ms_per_launch": kms, "traffic": None,
+                "peak_source": pk["src"] + " (burst: kernel timed alone)", "ms_per_launch": kms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, from the committed
+                # ncu --set full capture profiles/r01_layer_ncu_full.md (algorithmic: A 0.310 + out 1.239 + W 0.005 GB)
+                "traffic": 1.503e9 if (M, inter, d) == (201728, 3072, 768) else None,
                 "model_frac_sustained": value / n_gpus * GFLOP_PER_IMG[args.workload] / 1e3 / pk["tf_sustained"]}
         del a, w, b, o
+
+    # ------------------------------------------------------------------ batch-1 latency (BASELINE metric: bs1 p50)
+    lat = None
+    if rank == 0:
+        x1 = x[:1].contiguous()
+        for _ in range(30):
+            model.forward_graphed(x1)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(200):                      # sync-bracketed wall clock per run, as utils.py:866-872 times a model
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.forward_graphed(x1)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        lat = {"batch": 1, "p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "runs": len(ts),
+               "how": "CUDA-graph replay of the forward incl. the device-side input copy, host wall clock around each run"}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -289,6 +310,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
+            "latency": lat,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
