@@ -27,6 +27,8 @@ class PipelinedClassifier:
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._free = [torch.cuda.Event() for _ in range(2)]
+        self._host_out = None
+        self._pinned_out = {}
 
     @torch.no_grad()
     def _run(self, host_pixels: torch.Tensor, want_logits: bool):
@@ -37,11 +39,24 @@ class PipelinedClassifier:
         main = torch.cuda.current_stream(self.device)
         out = torch.empty((B, c.num_labels) if want_logits else (B,), dtype=torch.float32 if want_logits else torch.int64,
                           device=self.device)
-        n = (B + self.chunk - 1) // self.chunk
+        # Chunk schedule: the first H2D copy cannot overlap anything, so the chunks ramp up geometrically (chunk/8, /4, /2,
+        # then full chunks): every later copy hides behind the forward of the chunk before it (a forward costs ~3x its
+        # copy per image), and only the first small copy is exposed.
+        bounds, s0, size = [], 0, max(1, min(self.chunk, max(64, self.chunk // 8)))
+        while s0 < B:
+            e0 = min(B, s0 + size)
+            bounds.append((s0, e0))
+            s0, size = e0, min(self.chunk, size * 2)
+        host_out = None
+        if want_logits and host_pixels.is_pinned():
+            # pinned result buffer, allocated once per batch size (cudaHostAlloc costs milliseconds); the caller owns the
+            # returned tensor until the next call with the same batch size
+            host_out = self._pinned_out.get(B)
+            if host_out is None:
+                host_out = self._pinned_out[B] = torch.empty((B, c.num_labels), dtype=torch.float32).pin_memory()
         for k in range(2):
             self._free[k].record(main)
-        for i in range(n):
-            s, e = i * self.chunk, min(B, (i + 1) * self.chunk)
+        for i, (s, e) in enumerate(bounds):
             k = i & 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._free[k])          # buffer k no longer read by forward i-2
@@ -51,14 +66,24 @@ class PipelinedClassifier:
             lg = self.model(self._bufs[k][: e - s]).logits
             if want_logits:
                 out[s:e] = lg
+                if host_out is not None:
+                    host_out[s:e].copy_(out[s:e], non_blocking=True)   # D2H of this chunk overlaps the next forward
             else:
                 out[s:e] = lg.argmax(dim=-1)
             self._free[k].record(main)
+        if host_out is not None:
+            self._host_out = host_out
         return out
 
     def logits(self, host_pixels: torch.Tensor) -> torch.Tensor:
         """[B, num_labels] f32 on the HOST (synchronises)."""
-        return self._run(host_pixels, True).cpu()
+        self._host_out = None
+        dev_out = self._run(host_pixels, True)
+        if self._host_out is not None:                       # pinned input: chunk-wise async D2H already queued
+            torch.cuda.current_stream(self.device).synchronize()
+            out, self._host_out = self._host_out, None
+            return out.clone() if out.numel() < (1 << 22) else out   # small results: hand out a private copy
+        return dev_out.cpu()
 
     def predict(self, host_pixels: torch.Tensor) -> torch.Tensor:
         """argmax class ids [B] on the HOST; only 8 bytes per image cross PCIe on the way back."""

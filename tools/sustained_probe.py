@@ -54,38 +54,42 @@ def sustained(name, fn, flops=0.0, nbytes=0.0, secs=1.5):
     return ms
 
 
-x = torch.randn(M, D, device="cuda")
-g, b0 = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
-wqkv = (torch.randn(3 * D, D, device="cuda") * 0.02).bfloat16()
-wo = (torch.randn(D, D, device="cuda") * 0.02).bfloat16()
-w1 = (torch.randn(I, D, device="cuda") * 0.02).bfloat16()
-w2 = (torch.randn(D, I, device="cuda") * 0.02).bfloat16()
-bq, bo, b1, b2 = (torch.zeros(n, device="cuda") for n in (3 * D, D, I, D))
-xn = ops.layernorm(x, g, b0, 1e-12)
-qkv = ops.linear(xn, wqkv, bq)
-ctx = ops.attention(qkv, B, S, H)
-h = ops.linear(xn, w1, b1, act="gelu_erf")
-t = {}
-t["ln"] = sustained("layernorm", lambda: ops.layernorm(x, g, b0, 1e-12), nbytes=M * D * 6)
-t["qkv"] = sustained("qkv", lambda: ops.linear(xn, wqkv, bq, out=qkv), flops=2.0 * M * 3 * D * D)
-t["attn"] = sustained("attention", lambda: ops.attention(qkv, B, S, H), flops=4.0 * S * S * 64 * H * B)
-t["proj"] = sustained("out-proj", lambda: ops.linear(ctx, wo, bo, residual=x, out=x, out_dtype=torch.float32), flops=2.0 * M * D * D)
-t["fc1"] = sustained("fc1+gelu", lambda: ops.linear(xn, w1, b1, act="gelu_erf", out=h), flops=2.0 * M * I * D)
-t["fc2"] = sustained("fc2", lambda: ops.linear(h, w2, b2, residual=x, out=x, out_dtype=torch.float32), flops=2.0 * M * D * I)
-layer = t["qkv"] + t["attn"] + t["proj"] + t["fc1"] + t["fc2"] + 2 * t["ln"]
-print(f"layer {layer:.3f} ms -> {B / (12 * layer) * 1e3:.0f} img/s encoder-only (sustained, kernel by kernel)")
+def main():
+    x = torch.randn(M, D, device="cuda")
+    g, b0 = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    wqkv = (torch.randn(3 * D, D, device="cuda") * 0.02).bfloat16()
+    wo = (torch.randn(D, D, device="cuda") * 0.02).bfloat16()
+    w1 = (torch.randn(I, D, device="cuda") * 0.02).bfloat16()
+    w2 = (torch.randn(D, I, device="cuda") * 0.02).bfloat16()
+    bq, bo, b1, b2 = (torch.zeros(n, device="cuda") for n in (3 * D, D, I, D))
+    xn = ops.layernorm(x, g, b0, 1e-12)
+    qkv = ops.linear(xn, wqkv, bq)
+    ctx = ops.attention(qkv, B, S, H)
+    h = ops.linear(xn, w1, b1, act="gelu_erf")
+    t = {}
+    t["ln"] = sustained("layernorm", lambda: ops.layernorm(x, g, b0, 1e-12), nbytes=M * D * 6)
+    t["qkv"] = sustained("qkv", lambda: ops.linear(xn, wqkv, bq, out=qkv), flops=2.0 * M * 3 * D * D)
+    t["attn"] = sustained("attention", lambda: ops.attention(qkv, B, S, H), flops=4.0 * S * S * 64 * H * B)
+    t["proj"] = sustained("out-proj", lambda: ops.linear(ctx, wo, bo, residual=x, out=x, out_dtype=torch.float32), flops=2.0 * M * D * D)
+    t["fc1"] = sustained("fc1+gelu", lambda: ops.linear(xn, w1, b1, act="gelu_erf", out=h), flops=2.0 * M * I * D)
+    t["fc2"] = sustained("fc2", lambda: ops.linear(h, w2, b2, residual=x, out=x, out_dtype=torch.float32), flops=2.0 * M * D * I)
+    layer = t["qkv"] + t["attn"] + t["proj"] + t["fc1"] + t["fc2"] + 2 * t["ln"]
+    print(f"layer {layer:.3f} ms -> {B / (12 * layer) * 1e3:.0f} img/s encoder-only (sustained, kernel by kernel)")
 
 
-def whole():
-    global xn
-    ops.layernorm(x, g, b0, 1e-12)
-    ops.linear(xn, wqkv, bq, out=qkv)
-    ops.attention(qkv, B, S, H)
-    ops.linear(ctx, wo, bo, residual=x, out=x, out_dtype=torch.float32)
-    ops.layernorm(x, g, b0, 1e-12)
-    ops.linear(xn, w1, b1, act="gelu_erf", out=h)
-    ops.linear(h, w2, b2, residual=x, out=x, out_dtype=torch.float32)
+    def whole():
+        ops.layernorm(x, g, b0, 1e-12)
+        ops.linear(xn, wqkv, bq, out=qkv)
+        ops.attention(qkv, B, S, H)
+        ops.linear(ctx, wo, bo, residual=x, out=x, out_dtype=torch.float32)
+        ops.layernorm(x, g, b0, 1e-12)
+        ops.linear(xn, w1, b1, act="gelu_erf", out=h)
+        ops.linear(h, w2, b2, residual=x, out=x, out_dtype=torch.float32)
 
 
-ms = sustained("layer", whole, flops=2.0 * M * (4 * D * D + 2 * D * I) + 4.0 * S * S * 64 * H * B, secs=3.0)
-print(f"whole layer {ms:.3f} ms -> {B / (12 * ms) * 1e3:.0f} img/s encoder-only")
+    ms = sustained("layer", whole, flops=2.0 * M * (4 * D * D + 2 * D * I) + 4.0 * S * S * 64 * H * B, secs=3.0)
+    print(f"whole layer {ms:.3f} ms -> {B / (12 * ms) * 1e3:.0f} img/s encoder-only")
+
+
+if __name__ == "__main__":
+    main()
