@@ -142,6 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       pe.bias = item - tile * p.k_splits == 0 ? p.bias : nullptr;
       const int m0 = (tile / p.tiles_n) * BM + quad * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
+      prefetch_bias<BN, OUT_F32>(pe, grp, lane, nt0);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;

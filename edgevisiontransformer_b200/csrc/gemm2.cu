@@ -152,6 +152,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quad * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
+      prefetch_bias<BN, OUT_F32>(p, grp, lane, nt0);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;

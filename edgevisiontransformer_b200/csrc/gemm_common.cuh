@@ -179,6 +179,22 @@ __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict
 }
 
 
+// Bias lines of this warp's chunks of the coming tile -> L1, issued before the accumulator wait: with 227 KB of shared
+// memory the L1 is tiny and the bias loads of the epilogue otherwise pay an L2 round trip per chunk (ncu: ~10 % of the
+// FC1 kernel's warp samples stalled on them).  No registers are held across the wait.
+template <int BN, bool OUT_F32>
+__device__ __forceinline__ void prefetch_bias(const GemmParams& p, int grp, int lane, int nt0) {
+  constexpr int CH = OUT_F32 ? 32 : 64;
+  constexpr int NCH = BN / CH;
+  if (p.bias == nullptr) return;
+  // lane l covers 32-float (128-byte) line l of the warp's chunks: chunk k of this warp = grp + 2 k
+  constexpr int kLinesPerChunk = CH / 32;
+  const int k = lane / kLinesPerChunk;
+  const int c = grp + 2 * k;
+  const int col = nt0 + c * CH + (lane % kLinesPerChunk) * 32;
+  if (c < NCH && col < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + col));
+}
+
 // Epilogue of one 32-row x BN-column accumulator block by one warp.  Warp w reads TMEM lanes 32*(w%4).. (the
 // hardware's lane-quadrant rule) and takes the 128-byte output chunks (64 bf16 / 32 f32 columns) c = grp, grp+2, ...
 // (grp = w/4), so two warps share every row block.  Thread == accumulator row while the bias / activation math runs
