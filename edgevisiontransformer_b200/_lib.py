@@ -19,6 +19,7 @@ ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
 DIALECT_HF, DIALECT_TF = 0, 1
 PREC_BF16, PREC_TF32 = 0, 1
 MAX_LAYERS = 64
+STAGES = ("embed", "layernorm", "qkv", "attention", "out_proj", "fc1", "fc2", "head")
 
 
 class ModelSpec(C.Structure):
@@ -66,6 +67,8 @@ SIGNATURES = {
     "evt_performer_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
     "evt_performer_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "evt_model_launches_per_forward": (_i, [_p]),
+    "evt_model_profile_begin": (_i, [_p]),
+    "evt_model_profile_end": (_i, [_p, C.POINTER(_f), C.POINTER(_i)]),
     "evt_model_destroy": (_i, [_p]),
 }
 

@@ -78,6 +78,11 @@ struct evt_model {
   uint8_t* w_cls = nullptr;
   float* b_cls = nullptr;
   std::vector<void*> allocs;
+  // evt_model_profile_begin/end: one event before the first launch and one after every launch of a forward
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;      // pool, reused across forwards
+  size_t prof_used = 0;
+  std::vector<std::pair<int, std::pair<size_t, size_t>>> prof_spans;  // (stage, (event before, event after))
 };
 
 namespace evt {
@@ -246,6 +251,7 @@ extern "C" int evt_model_create(const evt_model_spec* spec, evt_model** out) {
 extern "C" int evt_model_destroy(evt_model* m) {
   if (!m) return EVT_OK;
   for (void* p : m->allocs) cudaFree(p);
+  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
   return EVT_OK;
 }
@@ -373,6 +379,25 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
     rc = (expr);      \
     if (rc != EVT_OK) return rc; \
   } while (0)
+  // profiling tap: events on the launching stream between launches (no effect on the launches themselves)
+  auto mark = [&](int stage) -> int {
+    if (!m->profiling) return EVT_OK;
+    if (m->prof_used == m->prof_events.size()) {
+      cudaEvent_t ev;
+      EVT_CUDA(cudaEventCreate(&ev));
+      m->prof_events.push_back(ev);
+    }
+    EVT_CUDA(cudaEventRecord(m->prof_events[m->prof_used], st));
+    if (stage >= 0) m->prof_spans.push_back({stage, {m->prof_used - 1, m->prof_used}});
+    ++m->prof_used;
+    return EVT_OK;
+  };
+#define EVT_STAGE(stage, expr) \
+  do {                         \
+    EVT_TRY(expr);             \
+    EVT_TRY(mark(stage));      \
+  } while (0)
+  EVT_TRY(mark(-1));
   const bool tf32 = s.precision == EVT_PREC_TF32;
   const int dt = tf32 ? EVT_F32 : EVT_BF16;   // GEMM operand type
   const int adt = tf32 ? EVT_TF32 : EVT_BF16;  // type activations are WRITTEN in (tf32: f32 storage, rounded to nearest)
@@ -381,15 +406,15 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   int64_t pm_ld = patch_ld;
   if (pm == nullptr) {
     EVT_CHECK_ARG(s.embed_k == 0, "this model takes a caller-built patch matrix (evt_model_forward_embedded)");
-    EVT_TRY(im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
+    EVT_STAGE(EVT_STAGE_EMBED, im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
     pm = w.big;
     pm_ld = m->patch_k;
   } else {
     EVT_CHECK_ARG(pm_ld >= m->patch_k, "patch matrix leading dimension smaller than the embedding K");
   }
-  EVT_TRY(gemm_launch(pm, pm_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
+  EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(pm, pm_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
                       w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
-  EVT_TRY(prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
+  EVT_STAGE(EVT_STAGE_EMBED, prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
   // encoder.  EXPERIMENTAL (EVT_FUSE_LN=1, off by default): with bf16 operands and the HF dataflow the LayerNorm that
   // FOLLOWS each residual projection can run inside that GEMM's epilogue (gemm3.cu).  It is bit-identical on the residual
   // stream but measured SLOWER on B200 (0.42 vs 0.22 ms for out-proj + LN at 100k rows): the second pass over the new
@@ -401,38 +426,38 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
     const LayerW& lw = m->layers[l];
     const int a = lw.a;
     if (!xn_ready)
-      EVT_TRY(layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+      EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
     xn_ready = false;
-    EVT_TRY(gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
+    EVT_STAGE(EVT_STAGE_QKV, gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
                         EVT_ACT_NONE, st));
     if (tf32)
-      EVT_TRY(attention_tf32_launch(reinterpret_cast<const float*>(w.qkv), 3 * a, reinterpret_cast<float*>(w.ctx), a, nullptr,
+      EVT_STAGE(EVT_STAGE_ATTN, attention_tf32_launch(reinterpret_cast<const float*>(w.qkv), 3 * a, reinterpret_cast<float*>(w.ctx), a, nullptr,
                                     batch, s.tokens, s.heads[l], s.head_size, scale, st));
     else
-      EVT_TRY(attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
+      EVT_STAGE(EVT_STAGE_ATTN, attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
     if (fuse_ln) {
-      EVT_TRY(gemm_res_ln_launch(w.ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
+      EVT_STAGE(EVT_STAGE_OPROJ, gemm_res_ln_launch(w.ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
     } else {
-      EVT_TRY(gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
+      EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
                           EVT_ACT_NONE, st));
-      EVT_TRY(layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+      EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
     }
-    EVT_TRY(gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
+    EVT_STAGE(EVT_STAGE_FC1, gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
                         st));
     if (fuse_ln && l + 1 < s.layers) {
       const LayerW& nx = m->layers[l + 1];
-      EVT_TRY(gemm_res_ln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, w.xn, D,
+      EVT_STAGE(EVT_STAGE_FC2, gemm_res_ln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, w.xn, D,
                                  M, D, lw.inter, st));
       xn_ready = true;
     } else {
-      EVT_TRY(gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M,
+      EVT_STAGE(EVT_STAGE_FC2, gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M,
                           D, lw.inter, EVT_ACT_NONE, st));
     }
   }
   // head: only the cls row of every image is consumed (SITE/models/vit/modeling_vit.py:641)
   const int64_t tok_stride = static_cast<int64_t>(s.tokens) * D;
   if (s.final_ln) {
-    EVT_TRY(layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, adt, D, nullptr, batch, D, s.eps, st));
+    EVT_STAGE(EVT_STAGE_HEAD, layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, adt, D, nullptr, batch, D, s.eps, st));
   } else {
     const long long total = static_cast<long long>(batch) * D;
     const unsigned grid = static_cast<unsigned>((total + 255) / 256);
@@ -444,18 +469,45 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
       EVT_CUDA(launch_pdl(gather_rows_cast_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, pdl_for_rows(M), static_cast<const float*>(w.resid),
                           tok_stride, reinterpret_cast<__nv_bfloat16*>(w.clsn), nrows, D));
     EVT_LAUNCH_CHECK("gather_rows_cast");
+    EVT_TRY(mark(EVT_STAGE_HEAD));
   }
   if (s.head_hidden > 0) {
     const int hl = padn(s.head_hidden, m->pad);
-    EVT_TRY(gemm_launch(w.clsn, D, m->w_pre, D, dt, m->b_pre, nullptr, 0, 0, 0, w.hh, adt, hl, 0, 0, 0, batch, s.head_hidden, D,
+    EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.clsn, D, m->w_pre, D, dt, m->b_pre, nullptr, 0, 0, 0, w.hh, adt, hl, 0, 0, 0, batch, s.head_hidden, D,
                         EVT_ACT_GELU_TANH, st));
-    EVT_TRY(gemm_launch(w.hh, hl, m->w_cls, hl, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
+    EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.hh, hl, m->w_cls, hl, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
                         s.num_labels, s.head_hidden, EVT_ACT_NONE, st));
   } else {
-    EVT_TRY(gemm_launch(w.clsn, D, m->w_cls, D, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
+    EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.clsn, D, m->w_cls, D, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
                         s.num_labels, D, EVT_ACT_NONE, st));
   }
+#undef EVT_STAGE
 #undef EVT_TRY
+  return EVT_OK;
+}
+
+extern "C" int evt_model_profile_begin(evt_model* m) {
+  EVT_CHECK_ARG(m != nullptr, "evt_model_profile_begin: model is null");
+  m->profiling = true;
+  m->prof_used = 0;
+  m->prof_spans.clear();
+  return EVT_OK;
+}
+
+extern "C" int evt_model_profile_end(evt_model* m, float* stage_ms, int* stage_launches) {
+  EVT_CHECK_ARG(m != nullptr && stage_ms != nullptr && stage_launches != nullptr, "evt_model_profile_end: null argument");
+  if (!m->profiling) return fail(EVT_ERR_STATE, "evt_model_profile_end without evt_model_profile_begin");
+  m->profiling = false;
+  for (int i = 0; i < EVT_STAGE_COUNT; ++i) stage_ms[i] = 0.f, stage_launches[i] = 0;
+  if (m->prof_used > 0) EVT_CUDA(cudaEventSynchronize(m->prof_events[m->prof_used - 1]));
+  for (const auto& sp : m->prof_spans) {
+    float ms = 0.f;
+    EVT_CUDA(cudaEventElapsedTime(&ms, m->prof_events[sp.second.first], m->prof_events[sp.second.second]));
+    stage_ms[sp.first] += ms;
+    stage_launches[sp.first] += 1;
+  }
+  m->prof_spans.clear();
+  m->prof_used = 0;
   return EVT_OK;
 }
 

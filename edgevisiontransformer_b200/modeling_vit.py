@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -311,6 +311,18 @@ class B200ViTForImageClassification(nn.Module):
 
     def launches_per_forward(self) -> int:
         return int(self._lib.evt_model_launches_per_forward(self._handle))
+
+    # ------------------------------------------------------------------ measurement aid
+    def profile_begin(self) -> None:
+        """Forwards issued from now on record a CUDA event after every launch (evt_model_profile_begin)."""
+        _lib.check(self._lib.evt_model_profile_begin(self._handle), "profile_begin")
+
+    def profile_end(self) -> Dict[str, Tuple[float, int]]:
+        """-> {stage: (summed device ms, launches)} over the forwards since profile_begin(); synchronises."""
+        n = len(_lib.STAGES)
+        ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+        _lib.check(self._lib.evt_model_profile_end(self._handle, ms, cnt), "profile_end")
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.STAGES)}
 
 
 def _first(v):

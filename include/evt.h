@@ -228,6 +228,23 @@ int evt_model_forward_embedded(evt_model* m, const void* patch_matrix, int64_t l
                                void* workspace, size_t workspace_bytes, evt_stream stream);
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int evt_model_launches_per_forward(const evt_model* m);
+/* Measurement aid (bench.py's roofline): between begin and end every forward on `m` records a CUDA event on its
+ * stream before its first launch and after every launch.  end synchronises on the last event, adds the elapsed time
+ * between consecutive events to the stage of the launch they bracket (sum over all forwards since begin) and returns
+ * the number of launches per stage.  Forwards issued while profiling is on must not be stream-captured. */
+enum evt_stage {
+  EVT_STAGE_EMBED = 0,  /* im2col, patch GEMM, cls/pos rows   */
+  EVT_STAGE_LN = 1,     /* layernorm_before / layernorm_after */
+  EVT_STAGE_QKV = 2,
+  EVT_STAGE_ATTN = 3,
+  EVT_STAGE_OPROJ = 4,
+  EVT_STAGE_FC1 = 5,
+  EVT_STAGE_FC2 = 6,
+  EVT_STAGE_HEAD = 7,   /* final LN on cls rows + classifier  */
+  EVT_STAGE_COUNT = 8
+};
+int evt_model_profile_begin(evt_model* m);
+int evt_model_profile_end(evt_model* m, float* stage_ms /* [EVT_STAGE_COUNT] */, int* stage_launches /* [EVT_STAGE_COUNT] */);
 int evt_model_destroy(evt_model* m);
 
 #ifdef __cplusplus

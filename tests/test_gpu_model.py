@@ -172,3 +172,25 @@ def test_t2t_front_end_and_model():
     assert r["max_abs"] <= 3e-2 and r["top1_agree"] == 1.0, r
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 224, 224, device="cuda"))
+
+
+def test_stage_profile_tap():
+    """evt_model_profile_begin/end: launches are attributed to the eight stages, results are unchanged by the tap."""
+    spec = ViTSpec.deit("tiny")
+    sd = ovit.state_dict_of(ovit.build_hf_model(spec, seed=0, stress=True))
+    m = _model(sd)
+    x = ovit.synthetic_images(4, seed=2).cuda()
+    ref = m(x).logits.clone()
+    m.profile_begin()
+    got = m(x).logits
+    got2 = m(x).logits
+    st = m.profile_end()
+    _check(got2, ref.cpu(), tol=5e-3)
+    _check(got, ref.cpu(), tol=5e-3)             # split-K reduce order may differ run to run (include/evt.h)
+    L = spec.layers
+    assert {k: n for k, (_, n) in st.items()} == {"embed": 6, "layernorm": 4 * L, "qkv": 2 * L, "attention": 2 * L,
+                                                  "out_proj": 2 * L, "fc1": 2 * L, "fc2": 2 * L, "head": 4}
+    assert all(ms > 0 for ms, _ in st.values())
+    assert sum(n for _, n in st.values()) == 2 * m.launches_per_forward()
+    with pytest.raises(RuntimeError):
+        m.profile_end()                           # not begun
