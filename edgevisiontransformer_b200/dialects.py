@@ -7,6 +7,10 @@ TF dialect facts handled here (modeling/models/vit.py:9-55, modeling/layers/atte
   * patch pixels flattened ``(p1 p2 c)``                           -> rows permuted to ``(c p1 p2)`` (our im2col order)
   * no final LayerNorm, head = Dense(mlp_dim, gelu) -> Dense(classes) -> pre_classifier + classifier
 The different skip-connection semantics (skip carries LN(x)) is a runtime flag (dialect="tf").
+
+timm / facebookresearch-deit dialect (``torch.hub.load('facebookresearch/deit:main', 'deit_*_patch16_224')``,
+utils.py:52-62, tools.py:244-263): same function as HF ViT with a fused ``attn.qkv`` Linear (rows q | k | v, head-major
+inside each), LayerNorm eps 1e-6 and flat key names -> pure renaming + split, see ``timm_vit_to_canonical``.
 """
 from __future__ import annotations
 
@@ -53,3 +57,42 @@ def tf_vit_to_canonical(sd: Dict[str, torch.Tensor], heads: List[int], head_size
     out["classifier.bias"] = sd["mlp_head.1.bias"]
     kw = dict(dialect="tf", hidden_act="gelu_tanh", layer_norm_eps=1e-5, final_ln=False, head_size=head_size, patch_size=patch)
     return out, kw
+
+
+def timm_vit_to_canonical(sd: Dict[str, torch.Tensor], patch: int = 16) -> Tuple[Dict[str, torch.Tensor], dict]:
+    """timm ``VisionTransformer`` / facebookresearch DeiT state dict -> (canonical state dict, from_state_dict kwargs).
+
+    Accepts the hub checkpoints' ``{'model': state_dict}`` wrapper.  Distilled variants (``dist_token`` / ``head_dist``)
+    are not what the reference loads (utils.py:52-62 asks for ``deit_{type}_patch16_{224,384}``) and are rejected."""
+    if "model" in sd and isinstance(sd["model"], dict):
+        sd = sd["model"]
+    if "dist_token" in sd or "head_dist.weight" in sd:
+        raise ValueError("distilled DeiT checkpoints (dist_token / head_dist) are not supported")
+    D = sd["cls_token"].shape[-1]
+    out: Dict[str, torch.Tensor] = {
+        "vit.embeddings.cls_token": sd["cls_token"].reshape(1, 1, D),
+        "vit.embeddings.position_embeddings": sd["pos_embed"].reshape(1, -1, D),
+        "vit.embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
+        "vit.embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
+        "vit.layernorm.weight": sd["norm.weight"], "vit.layernorm.bias": sd["norm.bias"],
+        "classifier.weight": sd["head.weight"], "classifier.bias": sd["head.bias"],
+    }
+    l = 0
+    while f"blocks.{l}.attn.qkv.weight" in sd:
+        p, q = f"blocks.{l}.", f"vit.encoder.layer.{l}."
+        w = sd[p + "attn.qkv.weight"]
+        if w.shape[0] != 3 * D:
+            raise ValueError(f"blocks.{l}.attn.qkv.weight has {w.shape[0]} rows, expected 3 x {D}")
+        b = sd.get(p + "attn.qkv.bias")
+        for i, n in enumerate(("query", "key", "value")):
+            out[q + f"attention.attention.{n}.weight"] = w[i * D:(i + 1) * D].contiguous()
+            if b is not None:
+                out[q + f"attention.attention.{n}.bias"] = b[i * D:(i + 1) * D].contiguous()
+        for src, dst in (("attn.proj", "attention.output.dense"), ("mlp.fc1", "intermediate.dense"), ("mlp.fc2", "output.dense"),
+                         ("norm1", "layernorm_before"), ("norm2", "layernorm_after")):
+            out[q + dst + ".weight"] = sd[p + src + ".weight"]
+            out[q + dst + ".bias"] = sd[p + src + ".bias"]
+        l += 1
+    if l == 0:
+        raise ValueError("not a timm VisionTransformer state dict (no blocks.0.attn.qkv.weight)")
+    return out, dict(layer_norm_eps=1e-6, hidden_act="gelu", patch_size=patch)

@@ -177,6 +177,18 @@ class B200ViTForImageClassification(nn.Module):
         return cls(config, sd, **kw)
 
     @classmethod
+    def from_timm(cls, model_or_state_dict, **kw):
+        """Build from a timm / facebookresearch-deit ``VisionTransformer`` (the model ``utils.get_torch_deit`` returns,
+        utils.py:52-62) or its state dict: fused qkv, LayerNorm eps 1e-6 (dialects.timm_vit_to_canonical)."""
+        from .dialects import timm_vit_to_canonical
+        sd = model_or_state_dict.state_dict() if hasattr(model_or_state_dict, "state_dict") else model_or_state_dict
+        image = kw.pop("image_size", None)
+        csd, cfg_kw = timm_vit_to_canonical({k: v for k, v in sd.items()}, patch=kw.pop("patch_size", 16))
+        if image is None:                       # 224 -> 197 tokens, 384 -> 577 (rejected by the library: > 256 tokens)
+            image = int(round((csd["vit.embeddings.position_embeddings"].shape[1] - 1) ** 0.5)) * cfg_kw["patch_size"]
+        return cls.from_state_dict(csd, image_size=image, **cfg_kw, **kw)
+
+    @classmethod
     def from_pretrained(cls, model_dir: str, **kw):
         from .checkpoint import load_checkpoint
         sd, cfg_kw = load_checkpoint(model_dir)

@@ -94,6 +94,16 @@ def gen_hf():
                             gelu=spec.gelu, eps=spec.eps)
 
 
+def gen_timm():
+    """timm / facebookresearch-deit dialect: HF forward with eps 1e-6 (the same function, see oracle/timm_vit.py)."""
+    spec = ViTSpec.deit("tiny", eps=1e-6)
+    model = ovit.build_hf_model(spec, seed=5, stress=True)
+    x = ovit.synthetic_images(2, seed=1)
+    with torch.no_grad():
+        logits = model(pixel_values=x).logits
+    np.savez_compressed(os.path.join(HERE, "timm_tiny_s5.npz"), logits=logits.numpy(), seed=5, batch=2)
+
+
 def gen_pruned():
     """Vendored optimize_model + head pruning applied to the live HF module."""
     sys.path.insert(0, os.path.join(REF, "deit_pruning/vendor/nn_pruning_v1"))
@@ -143,4 +153,5 @@ if __name__ == "__main__":
     gen_torch_layers()
     gen_hf()
     gen_pruned()
+    gen_timm()
     print("fixtures written to", HERE)

@@ -194,3 +194,19 @@ def test_stage_profile_tap():
     assert sum(n for _, n in st.values()) == 2 * m.launches_per_forward()
     with pytest.raises(RuntimeError):
         m.profile_end()                           # not begun
+
+
+def test_timm_dialect(golden_dir):
+    """timm / facebookresearch-deit checkpoints (fused qkv, eps 1e-6): utils.py:52-62, tools.py:244-263."""
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    from oracle import timm_vit as otimm
+    sd = ovit.state_dict_of(ovit.build_hf_model(ViTSpec.deit("tiny", eps=1e-6), seed=5, stress=True))
+    tsd = otimm.hf_to_timm(sd)
+    x = ovit.synthetic_images(2, seed=1)
+    want = otimm.timm_vit_forward(tsd, x, num_heads=3)
+    m = B200ViTForImageClassification.from_timm(tsd)
+    assert m.config.layer_norm_eps == 1e-6 and m.config.heads == [3] * 12 and m.config.image_size == 224
+    got = m(x.cuda()).logits
+    _check(got, want)
+    _check(got, torch.from_numpy(np.load(os.path.join(golden_dir, "timm_tiny_s5.npz"))["logits"]))
+    _check(B200ViTForImageClassification.from_timm(tsd, precision="tf32")(x.cuda()).logits, want, tol=1e-3)

@@ -116,3 +116,35 @@ def test_tf_dialect_and_t2t_shapes():
     assert torch.allclose(w @ w.t(), 32.0 * torch.eye(32), atol=1e-3)
     tab = ot2t.sinusoid_table(197, 384)
     assert tab.shape == (197, 384) and float(tab[0, 0]) == 0.0 and float(tab[0, 1]) == 1.0
+
+
+def test_timm_restatement_matches_hf(golden_dir):
+    """oracle.timm_vit (restated timm VisionTransformer) == the HF forward with eps 1e-6 on converted weights."""
+    from oracle import timm_vit as otimm
+    spec = ViTSpec.deit("tiny", eps=1e-6)
+    hf = ovit.build_hf_model(spec, seed=5, stress=True)
+    tsd = otimm.hf_to_timm(ovit.state_dict_of(hf))
+    assert tsd["blocks.0.attn.qkv.weight"].shape == (576, 192)
+    x = ovit.synthetic_images(2, seed=1)
+    got = otimm.timm_vit_forward(tsd, x, num_heads=3)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    assert (got - want).abs().max() < 1e-5
+    f = np.load(os.path.join(golden_dir, "timm_tiny_s5.npz"))
+    assert np.abs(got.numpy() - f["logits"]).max() < 1e-5
+
+
+def test_timm_adapter_roundtrip():
+    """dialects.timm_vit_to_canonical is the inverse of the HF -> timm renaming (host logic, no GPU)."""
+    from edgevisiontransformer_b200.dialects import timm_vit_to_canonical
+    from oracle import timm_vit as otimm
+    sd = ovit.state_dict_of(ovit.build_hf_model(ViTSpec.deit("tiny", eps=1e-6), seed=5, stress=True))
+    csd, kw = timm_vit_to_canonical({"model": otimm.hf_to_timm(sd)})
+    assert kw["layer_norm_eps"] == 1e-6 and kw["hidden_act"] == "gelu"
+    assert set(csd) == set(sd)
+    for k in sd:
+        assert torch.equal(csd[k], sd[k]), k
+    bad = otimm.hf_to_timm(sd)
+    bad["dist_token"] = torch.zeros(1, 1, 192)
+    with pytest.raises(ValueError):
+        timm_vit_to_canonical(bad)
