@@ -58,6 +58,9 @@ SIGNATURES = {
     "evt_prefix_tokens": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "evt_cast_f32_bf16": (_i, [_p, _p, _i64, _p]),
     "evt_unfold_nhwc": (_i, [_p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "evt_gather_layernorm": (_i, [_p, _p, _p, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _f, _p]),
+    "evt_window_attention_fwd": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _i, _i, _i, _f, _p]),
+    "evt_layernorm_mean_tokens": (_i, [_p, _p, _p, _p, _i64, _i, _i, _f, _p]),
     "evt_model_create": (_i, [C.POINTER(ModelSpec), C.POINTER(_p)]),
     "evt_model_load_weights": (_i, [_p, C.POINTER(TensorView), _i, _p]),
     "evt_model_workspace_bytes": (_i, [_p, _i, C.POINTER(_sz)]),

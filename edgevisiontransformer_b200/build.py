@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libevt.so")
 OBJ_DIR = os.path.join(CSRC, "build")
 
-SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "gemm3.cu", "attention.cu", "layernorm.cu", "embed.cu", "performer.cu", "model.cu"]
+SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "gemm3.cu", "attention.cu", "layernorm.cu", "embed.cu", "performer.cu", "swin.cu", "model.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

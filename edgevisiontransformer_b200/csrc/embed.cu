@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ops.h"
 #include "ptx.cuh"
 
 namespace evt {
@@ -131,9 +132,10 @@ int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, 
   EVT_CHECK_ARG(pixels && cols, "im2col: null pointer");
   EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && P > 0, "im2col: sizes must be positive");
   EVT_CHECK_ARG(H % P == 0 && W % P == 0, "im2col: image size must be a multiple of the patch size");
-  EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8");
   EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(pixels) % 16 == 0 && reinterpret_cast<uintptr_t>(cols) % 16 == 0,
                 "im2col: pointers must be 16-byte aligned");
+  if (P % 8 != 0 && P % 4 == 0 && out_dtype == EVT_BF16) return im2col4_launch(pixels, cols, B, H, W, P, st);  // Swin: P = 4
+  EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8 (bf16: of 4)");
   if (out_dtype == EVT_BF16) {
     const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
     EVT_CUDA(launch_pdl(im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,

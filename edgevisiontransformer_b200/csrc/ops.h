@@ -25,6 +25,7 @@ int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const
                      int64_t y_stride, float* y_copy, int64_t rows, int D, float eps, cudaStream_t st);
 
 int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st);
+int im2col4_launch(const float* pixels, void* cols, int B, int H, int W, int P, cudaStream_t st);  // swin.cu, P % 4 == 0
 int prefix_tokens_launch(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix, int D,
                          cudaStream_t st);
 int cast_launch(const float* x, void* y, int64_t n, cudaStream_t st);

@@ -163,6 +163,56 @@ def attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_size: int = 64
     return ctx
 
 
+def gather_layernorm(x: torch.Tensor, idx: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float,
+                     images: int, T_in: int, T_out: int, G: int = 1, out_dtype: Optional[torch.dtype] = torch.bfloat16,
+                     copy: bool = False):
+    """Row gather fused with LayerNorm (Swin window partition / shift / patch merging, include/evt.h).
+    x f32 [images*T_in, C]; idx int32 [T_out*G] -> (LN output [images*T_out, G*C] or None, raw gathered f32 copy or None)."""
+    _need_cuda(x, idx, gamma, beta)
+    if x.dtype != torch.float32 or x.dim() != 2 or not x.is_contiguous() or x.shape[0] != images * T_in:
+        raise ValueError("gather_layernorm wants a contiguous f32 [images*T_in, C] matrix")
+    if idx.dtype != torch.int32 or idx.numel() != T_out * G or not idx.is_contiguous():
+        raise ValueError("gather_layernorm: idx must be a contiguous int32 [T_out*G] tensor")
+    C = x.shape[1]
+    y = torch.empty((images * T_out, G * C), dtype=out_dtype, device=x.device) if out_dtype is not None else None
+    cp = torch.empty((images * T_out, G * C), dtype=torch.float32, device=x.device) if copy else None
+    lib = _lib.load()
+    _lib.check(lib.evt_gather_layernorm(x.data_ptr(), idx.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(y),
+                                        _dt(y) if y is not None else EVT_BF16, _ptr(cp), images, T_in, T_out, G, C, float(eps),
+                                        _stream()), "gather_layernorm")
+    return y, cp
+
+
+def window_attention(qkv: torch.Tensor, table: torch.Tensor, n_windows: int, heads: int, window_tokens: int = 49,
+                     head_size: int = 32, scale: Optional[float] = None) -> torch.Tensor:
+    """qkv bf16 [n_windows*49, 3*heads*32] in window order, table f32 [n_tab, heads, 64, 56] (log2 domain, include/evt.h)
+    -> ctx bf16 [n_windows*49, heads*32]."""
+    _need_cuda(qkv, table)
+    if qkv.dtype != torch.bfloat16 or qkv.dim() != 2 or qkv.stride(1) != 1 or qkv.shape[0] != n_windows * window_tokens:
+        raise ValueError("window_attention wants a bf16 [n_windows*tokens, 3*heads*head_size] matrix")
+    if table.dtype != torch.float32 or table.dim() != 4 or tuple(table.shape[1:]) != (heads, 64, 56) or not table.is_contiguous():
+        raise ValueError("window_attention: table must be a contiguous f32 [n_tab, heads, 64, 56] tensor")
+    ctx = torch.empty((qkv.shape[0], heads * head_size), dtype=torch.bfloat16, device=qkv.device)
+    scale = float(head_size ** -0.5 if scale is None else scale)
+    lib = _lib.load()
+    _lib.check(lib.evt_window_attention_fwd(qkv.data_ptr(), qkv.stride(0), ctx.data_ptr(), ctx.stride(0), table.data_ptr(),
+                                            table.shape[0], n_windows, window_tokens, heads, head_size, scale, _stream()),
+               "window_attention")
+    return ctx
+
+
+def layernorm_mean_tokens(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, images: int, T: int) -> torch.Tensor:
+    """mean over tokens of LayerNorm(x): x f32 [images*T, D] -> bf16 [images, D] (Swin final norm + pooler)."""
+    _need_cuda(x, gamma, beta)
+    if x.dtype != torch.float32 or x.dim() != 2 or not x.is_contiguous() or x.shape[0] != images * T:
+        raise ValueError("layernorm_mean_tokens wants a contiguous f32 [images*T, D] matrix")
+    y = torch.empty((images, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.evt_layernorm_mean_tokens(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), images, T, x.shape[1],
+                                             float(eps), _stream()), "layernorm_mean_tokens")
+    return y
+
+
 def im2col_patch(pixels: torch.Tensor, patch: int = 16) -> torch.Tensor:
     _need_cuda(pixels)
     if pixels.dtype != torch.float32 or pixels.dim() != 4 or pixels.shape[1] != 3:

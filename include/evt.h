@@ -136,7 +136,8 @@ int evt_attention_fwd_tf32(const float* qkv, int64_t ldq, float* ctx, int64_t ld
                            int B, int S, int heads, int head_size, float scale, evt_stream stream);
 
 /* Non-overlapping patch gather: pixels f32 NCHW [B,3,H,W] -> bf16 [B*(H/P)*(W/P), 3*P*P] with
- * K order (c, i, j) -- the im2col of Conv2d(3,D,P,P) (SITE/models/vit/modeling_vit.py:151-167). */
+ * K order (c, i, j) -- the im2col of Conv2d(3,D,P,P) (SITE/models/vit/modeling_vit.py:151-167).  P a multiple of 4
+ * (ViT / DeiT: 16; Swin: 4). */
 int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream);
 
 /* Rows [0, n_prefix) of each image's token block: out[b, t, :] = prefix[t, :] + pos[t, :]
@@ -166,6 +167,33 @@ int evt_unfold_ln_nhwc(const void* x, int x_dtype, void* out, int64_t ldo, const
 int evt_performer_workspace_bytes(int B, int T, size_t* out);
 int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace,
                       int B, int T, int emb, int m, float eps, evt_stream stream);
+
+/* ---- Swin shifted-window block (tools.py:265-292 export_onnx_swin, utils.py:14-47 get_swin; arithmetic:
+ * SITE/models/swin/modeling_swin.py).  Token rows are kept in the window order of the current block, see
+ * edgevisiontransformer_b200/modeling_swin.py. */
+
+/* Row gather fused with LayerNorm: output row r (image r / T_out, token t = r % T_out) is the concatenation of the G
+ * input rows  image * T_in + idx[t * G + g]  (g = 0..G-1, each C floats) of x, normalised over its G*C elements.
+ *   G = 1: window partition / cyclic shift / reverse (SwinLayer.forward :606-637) folded into layernorm_before;
+ *          copy_f32 (nullable) receives the gathered, un-normalised rows = the residual stream in the new order
+ *   G = 4: SwinPatchMerging (:326-349): 2x2 neighbourhood concat + LayerNorm(4C)
+ *   y (nullable when copy_f32 is given): bf16 or f32 [images * T_out, G*C]; idx: int32 [T_out * G] (device). */
+int evt_gather_layernorm(const float* x, const int* idx, const float* gamma, const float* beta, void* y, int y_dtype,
+                         float* copy_f32, int64_t images, int T_in, int T_out, int G, int C, float eps, evt_stream stream);
+
+/* Window attention (SwinSelfAttention.forward :410-459) for 7x7 windows, head size 32:
+ *   ctx = softmax(q k^T * scale + relative_position_bias + shift_mask) v   per (window, head)
+ *   qkv   : bf16 [n_windows * 49, ldq], columns q | k | v (heads*32 each), rows in window order
+ *   table : f32 [n_tab, heads, 64, 56] = (bias[h] + mask[w % n_tab]) * log2(e), key columns 49..55 = -inf, rows 49..63
+ *           finite; n_tab = windows per image for shifted blocks, 1 otherwise
+ *   ctx   : bf16 [n_windows * 49, ldc]. */
+int evt_window_attention_fwd(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* table, int n_tab,
+                             int64_t n_windows, int window_tokens, int heads, int head_size, float scale, evt_stream stream);
+
+/* y[image, :] (bf16) = mean over the T tokens of LayerNorm(x[image, t, :]) -- SwinModel.layernorm + AdaptiveAvgPool1d
+ * (:899-904).  x f32 [images, T, D]. */
+int evt_layernorm_mean_tokens(const float* x, const float* gamma, const float* beta, void* y, int64_t images, int T, int D,
+                              float eps, evt_stream stream);
 
 /* ------------------------------------------------------------------ model level ---------- */
 

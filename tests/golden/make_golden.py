@@ -104,6 +104,18 @@ def gen_timm():
     np.savez_compressed(os.path.join(HERE, "timm_tiny_s5.npz"), logits=logits.numpy(), seed=5, batch=2)
 
 
+def gen_swin():
+    """HF SwinForImageClassification (the transformers port of the model utils.get_swin builds) on seeded weights."""
+    from oracle import swin as osw
+    for name, kind, depths, seed, bs in [("swin_tiny_s7", "tiny", None, 7, 2), ("swin_tiny_d1131_s8", "tiny", [1, 1, 3, 1], 8, 1)]:
+        model = osw.build_hf_swin(kind, seed=seed, stress=True, depths=depths)
+        x = ovit.synthetic_images(bs, seed=1)
+        with torch.no_grad():
+            logits = model(pixel_values=x).logits
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), logits=logits.numpy(), seed=seed, batch=bs,
+                            depths=np.array(model.config.depths))
+
+
 def gen_pruned():
     """Vendored optimize_model + head pruning applied to the live HF module."""
     sys.path.insert(0, os.path.join(REF, "deit_pruning/vendor/nn_pruning_v1"))
@@ -154,4 +166,5 @@ if __name__ == "__main__":
     gen_hf()
     gen_pruned()
     gen_timm()
+    gen_swin()
     print("fixtures written to", HERE)

@@ -1,0 +1,85 @@
+"""GPU parity of the Swin shifted-window path (through the C ABI) against the CPU oracle (oracle/swin.py, pinned against
+the installed HF SwinForImageClassification) and against the committed fixtures.  bf16 mode: logits max-abs <= 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import swin as osw  # noqa: E402
+from oracle import vit as ovit  # noqa: E402
+
+LOG2E = 1.4426950408889634
+
+
+def test_gather_layernorm_matches_torch():
+    from edgevisiontransformer_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (B, T_in, T_out, G, C) in [(3, 196, 196, 1, 96), (2, 784, 196, 4, 192), (2, 196, 49, 4, 768), (1, 49, 49, 1, 384)]:
+        x = torch.randn(B * T_in, C, generator=g) * 2 + 0.5
+        idx = torch.stack([torch.randperm(T_in, generator=g)[:T_out] for _ in range(G)], 1).to(torch.int32).contiguous()
+        gamma, beta = torch.randn(G * C, generator=g), torch.randn(G * C, generator=g)
+        rows = torch.cat([x.view(B, T_in, C)[:, idx[:, j].long()] for j in range(G)], -1).reshape(B * T_out, G * C)
+        want = torch.nn.functional.layer_norm(rows, (G * C,), gamma, beta, 1e-5)
+        y, cp = ops.gather_layernorm(x.cuda(), idx.view(-1).cuda(), gamma.cuda(), beta.cuda(), 1e-5, B, T_in, T_out, G,
+                                     out_dtype=torch.float32, copy=True)
+        assert torch.equal(cp.cpu(), rows)                                  # the permuted residual stream is a bit-exact copy
+        assert (y.cpu() - want).abs().max() < 2e-5
+        yb, none = ops.gather_layernorm(x.cuda(), idx.view(-1).cuda(), gamma.cuda(), beta.cuda(), 1e-5, B, T_in, T_out, G)
+        assert none is None and (yb.float().cpu() - want).abs().max() < 0.04   # bf16 rounding of values up to ~6
+
+
+@pytest.mark.parametrize("heads,n_win,n_tab", [(3, 8, 4), (6, 5, 1), (24, 3, 1)])
+def test_window_attention_matches_torch(heads, n_win, n_tab):
+    from edgevisiontransformer_b200 import ops
+    from edgevisiontransformer_b200.modeling_swin import attention_table, shift_mask
+    g = torch.Generator().manual_seed(heads)
+    C = heads * 32
+    qkv = (torch.randn(n_win * 49, 3 * C, generator=g) * 1.5).bfloat16()
+    tab = torch.randn(169, heads, generator=g)
+    mask = shift_mask(14, 14, 7, 3) if n_tab == 4 else None
+    table = attention_table(tab, heads, 7, mask)
+    got = ops.window_attention(qkv.cuda(), table.cuda(), n_win, heads).float().cpu()
+    q, k, v = [t.float().view(n_win, 49, heads, 32).transpose(1, 2) for t in qkv.split(C, dim=1)]
+    s = q @ k.transpose(-1, -2) / 32 ** 0.5 + table[:, :, :49, :49][torch.arange(n_win) % n_tab] / LOG2E
+    want = (s.softmax(-1) @ v).transpose(1, 2).reshape(n_win * 49, C)
+    assert (got - want).abs().max() < 0.03          # bf16 probabilities and bf16 output, |v| up to ~6
+    assert (got - want).abs().mean() < 2e-3
+
+
+def test_layernorm_mean_tokens_matches_torch():
+    from edgevisiontransformer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for B, T, D in [(5, 49, 768), (2, 49, 1024), (3, 7, 96)]:
+        x = torch.randn(B * T, D, generator=g) * 3 - 1
+        gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+        want = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-5).view(B, T, D).mean(1)
+        got = ops.layernorm_mean_tokens(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5, B, T).float().cpu()
+        assert (got - want).abs().max() < 0.02      # bf16 output
+
+
+@pytest.mark.parametrize("name,depths,seed,bs", [("swin_tiny_s7", None, 7, 2), ("swin_tiny_d1131_s8", [1, 1, 3, 1], 8, 1)])
+def test_swin_matches_oracle_and_golden(golden_dir, name, depths, seed, bs):
+    from edgevisiontransformer_b200.modeling_swin import B200SwinForImageClassification, microsoft_to_hf
+    hf = osw.build_hf_swin("tiny", seed=seed, stress=True, depths=depths)
+    sd = ovit.state_dict_of(hf)
+    x = ovit.synthetic_images(bs + 1, seed=1)
+    want = osw.swin_forward(sd, x, hf.config.depths, hf.config.num_heads)
+    m = B200SwinForImageClassification.from_hf(hf, max_batch=2)       # bs + 1 images: exercises the chunk loop
+    got = m(pixel_values=x.cuda()).logits
+    r = ovit.compare_logits(got, want)
+    assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
+    f = np.load(os.path.join(golden_dir, name + ".npz"))
+    r = ovit.compare_logits(got[:bs], torch.from_numpy(f["logits"]))  # fixture from the HF forward itself
+    assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
+    # the microsoft/Swin-Transformer key dialect loads to the same function
+    m2 = B200SwinForImageClassification.from_microsoft(osw.hf_to_microsoft(sd), depths=hf.config.depths,
+                                                       num_heads=hf.config.num_heads, embed_dim=96)
+    assert torch.equal(m2(x[:1].cuda()).logits, m(x[:1].cuda()).logits)
+    assert m.num_parameters() == sum(p.numel() for p in hf.parameters())
+    with pytest.raises(RuntimeError):
+        m(x)                                                           # CPU input: no fallback
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 192, 192, device="cuda"))

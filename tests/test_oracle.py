@@ -148,3 +148,42 @@ def test_timm_adapter_roundtrip():
     bad["dist_token"] = torch.zeros(1, 1, 192)
     with pytest.raises(ValueError):
         timm_vit_to_canonical(bad)
+
+
+@pytest.mark.parametrize("name,depths,seed,bs", [("swin_tiny_s7", None, 7, 2), ("swin_tiny_d1131_s8", [1, 1, 3, 1], 8, 1)])
+def test_swin_restatement_matches_hf(golden_dir, name, depths, seed, bs):
+    """oracle.swin == installed HF SwinForImageClassification on the same seeded weights, and == the committed fixture."""
+    from oracle import swin as osw
+    hf = osw.build_hf_swin("tiny", seed=seed, stress=True, depths=depths)
+    sd = ovit.state_dict_of(hf)
+    x = ovit.synthetic_images(bs, seed=1)
+    got = osw.swin_forward(sd, x, hf.config.depths, hf.config.num_heads)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    assert (got - want).abs().max() < 1e-4
+    f = np.load(os.path.join(golden_dir, name + ".npz"))
+    assert np.abs(got.numpy() - f["logits"]).max() < 1e-4
+
+
+def test_swin_host_tables_and_key_adapter():
+    """Host logic of modeling_swin (no GPU): window-order tables == roll + window_partition, the shift mask and the padded
+    attention table == the reference construction, microsoft_to_hf inverts the renaming."""
+    from edgevisiontransformer_b200 import modeling_swin as ms
+    from oracle import swin as osw
+    for H, sh in ((14, 0), (14, 3), (28, 3), (7, 0)):
+        x = torch.arange(H * H).float().view(1, H, H, 1)
+        y = torch.roll(x, (-sh, -sh), (1, 2)) if sh else x
+        assert torch.equal(osw.window_partition(y, 7).view(-1).long(), ms.window_order(H, H, 7, sh))
+    assert torch.equal(ms.shift_mask(28, 28, 7, 3), osw.shift_mask(28, 28, 7, 3))
+    assert torch.equal(ms.relative_position_index(7), osw.relative_position_index(7))
+    tab = torch.randn(169, 3)
+    t = ms.attention_table(tab, 3, 7, ms.shift_mask(14, 14, 7, 3))
+    assert t.shape == (4, 3, 64, 56) and torch.isinf(t[..., 49:]).all() and (t[:, :, 49:, :49] == 0).all()
+    want = tab[osw.relative_position_index(7).view(-1)].view(49, 49, 3).permute(2, 0, 1)[None] + osw.shift_mask(14, 14, 7, 3)[:, None]
+    assert torch.allclose(t[:, :, :49, :49], want * ms.LOG2E)
+    sd = ovit.state_dict_of(osw.build_hf_swin("tiny", seed=1, depths=[1, 1, 1, 1]))
+    back = ms.microsoft_to_hf({"model": osw.hf_to_microsoft(sd)})
+    keys = {k for k in sd if not k.endswith("relative_position_index")}
+    assert set(back) == keys
+    for k in keys:
+        assert torch.equal(back[k], sd[k]), k
