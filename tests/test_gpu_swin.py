@@ -77,7 +77,8 @@ def test_swin_matches_oracle_and_golden(golden_dir, name, depths, seed, bs):
     # the microsoft/Swin-Transformer key dialect loads to the same function
     m2 = B200SwinForImageClassification.from_microsoft(osw.hf_to_microsoft(sd), depths=hf.config.depths,
                                                        num_heads=hf.config.num_heads, embed_dim=96)
-    assert torch.equal(m2(x[:1].cuda()).logits, m(x[:1].cuda()).logits)
+    r = ovit.compare_logits(m2(x[:1].cuda()).logits, want[:1])       # (not bit-equal run to run: split-K, include/evt.h)
+    assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
     assert m.num_parameters() == sum(p.numel() for p in hf.parameters())
     with pytest.raises(RuntimeError):
         m(x)                                                           # CPU input: no fallback
