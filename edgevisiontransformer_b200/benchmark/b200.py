@@ -21,6 +21,8 @@ import numpy as np
 import torch
 
 DEIT = {"deit_tiny": (192, 3, 768), "deit_small": (384, 6, 1536), "deit_base": (768, 12, 3072)}
+SWIN = {"swin_tiny": (96, [2, 2, 6, 2], [3, 6, 12, 24]), "swin_small": (96, [2, 2, 18, 2], [3, 6, 12, 24]),
+        "swin_base": (128, [2, 2, 18, 2], [4, 8, 16, 32])}         # swin_*_patch4_window7_224 (tools.py:280)
 T2T = {"t2t_vit_7": (256, 7, 4, 2.0), "t2t_vit_10": (256, 10, 4, 2.0), "t2t_vit_12": (256, 12, 4, 2.0),
        "t2t_vit_14": (384, 14, 6, 3.0)}
 
@@ -84,6 +86,15 @@ def build_model(name: str, precision: str = "bf16", max_batch: int = 512, device
         m = B200T2TViT(_random_t2t_weights(hidden, depth, heads, ratio), depth=depth, num_heads=heads, device=device,
                        max_batch=min(max_batch, 256), precision=precision)
         return m, (224, 224, 3), f"{name} random-init ({precision}), NHWC input"
+    if name in SWIN:
+        from transformers import SwinConfig, SwinForImageClassification
+        from ..modeling_swin import B200SwinForImageClassification
+        dim, depths, heads = SWIN[name]
+        torch.manual_seed(0)
+        hf = SwinForImageClassification(SwinConfig(image_size=224, patch_size=4, window_size=7, embed_dim=dim, depths=depths,
+                                                   num_heads=heads, num_labels=1000)).eval()
+        m = B200SwinForImageClassification.from_hf(hf, device=device, max_batch=min(max_batch, 256))
+        return m, (3, 224, 224), f"{name} random-init (bf16)"
     if name in ("attention", "ffn"):
         from .. import torch_layers as tl
         h, n = op_kw.get("h", 768), op_kw.get("n", 128)
@@ -125,7 +136,7 @@ def b200_benchmark(model, input_shape: Sequence[int], num_runs: int = 50, warmup
 
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="b200_benchmark", description=__doc__.split("\n")[0])
-    ap.add_argument("--model", required=True, help="deit_{tiny,small,base} | t2t_vit_{7,10,12,14} | attention | ffn | checkpoint dir")
+    ap.add_argument("--model", required=True, help="deit_{tiny,small,base} | swin_{tiny,small,base} | t2t_vit_{7,10,12,14} | attention | ffn | checkpoint dir")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--num_runs", type=int, default=50)

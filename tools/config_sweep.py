@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from edgevisiontransformer_b200 import B200ViTForImageClassification  # noqa: E402
 from edgevisiontransformer_b200.benchmark.b200 import _random_hf, _random_t2t_weights  # noqa: E402
 
-GF = {"tiny_bs1": 2.507, "small_bs256": 9.198, "base_bs4096": 35.128, "pruned_tiny_bs1024": 0.827, "t2t14_bs1024": 9.567}
+GF = {"swin_tiny_bs1024": 4.5, "tiny_bs1": 2.507, "small_bs256": 9.198, "base_bs4096": 35.128, "pruned_tiny_bs1024": 0.827, "t2t14_bs1024": 9.567}
 
 
 def pruned_tiny_state_dict():
@@ -61,11 +61,17 @@ def main():
         ("base_bs4096", "deit_base", 4096, 1024, "bf16"),
         ("pruned_tiny_bs1024", "pruned", 1024, 1024, "bf16"),
         ("t2t14_bs1024", "t2t_vit_14", 1024, 256, "bf16"),
+        ("swin_tiny_bs1024", "swin_tiny", 1024, 256, "bf16"),      # SURVEY.md section 8f rank 4 (not a BASELINE config)
     ]
     for name, kind, batch, chunk, prec in cases:
         if only and not any(o in name for o in only):
             continue
-        if kind == "t2t_vit_14":
+        if kind == "swin_tiny":
+            from edgevisiontransformer_b200.benchmark.b200 import build_model
+            model, _, _ = build_model("swin_tiny", max_batch=chunk)
+            x = torch.randn(batch, 3, 224, 224, device=dev)
+            tap = None
+        elif kind == "t2t_vit_14":
             from edgevisiontransformer_b200.modeling_t2t import B200T2TViT
             model = B200T2TViT(_random_t2t_weights(384, 14, 6, 3.0), depth=14, num_heads=6, device=dev, max_batch=chunk)
             x = torch.randn(batch, 224, 224, 3, device=dev)
