@@ -22,24 +22,36 @@ namespace {
 
 using namespace gemm_detail;
 
-template <int BN>
+#ifndef EVT_EPI_WARPS_ACT
+#define EVT_EPI_WARPS_ACT 8
+#endif
+constexpr int kEpiWarpsAct = EVT_EPI_WARPS_ACT;  // epilogue warps of the bf16-output kernels with a fused activation
+
+// EW = epilogue warps per CTA (8, or 16 = 4 per TMEM lane quadrant with one 64-column chunk each).  16 was tried for the
+// FC1 + GELU kernel (-DEVT_EPI_WARPS_ACT=16) on the theory that the epilogue's latency per tile holds up the accumulator
+// hand-off: it measured SLOWER (FC1 0.944 vs 0.912 ms in the step, 1101 vs 1248 TFLOP/s alone) -- 576 threads leave 96
+// registers per thread (the unrolled GELU loses its interleaving) and the extra staging costs a pipeline stage.  Default 8.
+template <int BN, int EW>
 struct Cfg2 {
   static constexpr int kABytes = BM * kStageRowBytes;
   static constexpr int kBBytes = (BN / 2) * kStageRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 6 : BN == 192 ? 6 : 8;
+  static constexpr int kStagingBytes = EW * kStgBytes;
+  static constexpr int kMaxStages = (232448 - 1024 - kStagingBytes - 256) / kStageBytes;
+  static constexpr int kStages = kMaxStages < (BN == 128 ? 8 : 6) ? kMaxStages : (BN == 128 ? 8 : 6);
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
-  static constexpr int kStagingBytes = kEpiWarps * kStgBytes;
+  static constexpr int kProducer = EW, kMma = EW + 1, kThreadsCta = 32 * (EW + 2);
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
-template <int BN, bool OUT_F32, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int BN, bool OUT_F32, int ACT, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (EW + 2), 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, EW>;
+  constexpr int kProducerWarp = C::kProducer, kMmaWarp = C::kMma, kEpiWarps = EW;
   extern __shared__ uint8_t smem_raw[];
   // The dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up below is identical in
   // the two CTAs -- required: the MMA and the multicast commits address the peer by shared-memory OFFSET.
@@ -152,11 +164,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quad * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
-      prefetch_bias<BN, OUT_F32>(p, grp, lane, nt0);
+      prefetch_bias<BN, OUT_F32, EW / 4>(p, grp, lane, nt0);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      epilogue_tile<BN, false, OUT_F32, ACT, true>(p, &tmO, stg, grp, lane, m0, nt0, t_row);
+      epilogue_tile<BN, false, OUT_F32, ACT, true, EW / 4>(p, &tmO, stg, grp, lane, m0, nt0, t_row);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(&tempty[as], 0));
@@ -180,8 +192,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, bool OUT_F32, int ACT>
 int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, GemmParams p, cudaStream_t stream) {
-  using C = Cfg2<BN>;
-  auto kern = gemm_pair_kernel<BN, OUT_F32, ACT>;
+  constexpr int EW = (ACT != EVT_ACT_NONE && !OUT_F32) ? kEpiWarpsAct : 8;
+  using C = Cfg2<BN, EW>;
+  constexpr int kThreads = C::kThreadsCta;
+  auto kern = gemm_pair_kernel<BN, OUT_F32, ACT, EW>;
   static int configured_dev = -1;
   static int max_pairs = 0;
   int dev = 0;

@@ -182,26 +182,26 @@ __device__ __forceinline__ void bias_act(float (&v)[CH], const float* __restrict
 // Bias lines of this warp's chunks of the coming tile -> L1, issued before the accumulator wait: with 227 KB of shared
 // memory the L1 is tiny and the bias loads of the epilogue otherwise pay an L2 round trip per chunk (ncu: ~10 % of the
 // FC1 kernel's warp samples stalled on them).  No registers are held across the wait.
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int NGRP = 2>
 __device__ __forceinline__ void prefetch_bias(const GemmParams& p, int grp, int lane, int nt0) {
   constexpr int CH = OUT_F32 ? 32 : 64;
   constexpr int NCH = BN / CH;
   if (p.bias == nullptr) return;
-  // lane l covers 32-float (128-byte) line l of the warp's chunks: chunk k of this warp = grp + 2 k
+  // lane l covers 32-float (128-byte) line l of the warp's chunks: chunk k of this warp = grp + NGRP k
   constexpr int kLinesPerChunk = CH / 32;
   const int k = lane / kLinesPerChunk;
-  const int c = grp + 2 * k;
+  const int c = grp + NGRP * k;
   const int col = nt0 + c * CH + (lane % kLinesPerChunk) * 32;
   if (c < NCH && col < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + col));
 }
 
 // Epilogue of one 32-row x BN-column accumulator block by one warp.  Warp w reads TMEM lanes 32*(w%4).. (the
 // hardware's lane-quadrant rule) and takes the 128-byte output chunks (64 bf16 / 32 f32 columns) c = grp, grp+2, ...
-// (grp = w/4), so two warps share every row block.  Thread == accumulator row while the bias / activation math runs
+// (grp = w/4; NGRP = epilogue warps / 4 groups share every row block: 2 in the 1-CTA kernels, up to 4 in the CTA-pair kernel).  Thread == accumulator row while the bias / activation math runs
 // on packed f32x2 pairs; the converted chunk then goes through a 128B-swizzled 4 KB smem tile (stg) to a TMA store /
 // TMA f32 reduce-add, or to coalesced global stores on the generic path.
 //   m0: first global row of this warp's block; nt0: first column of the tile; t_row: TMEM address (lane | column).
-template <int BN, bool TF32, bool OUT_F32, int ACT, bool TMA_OUT>
+template <int BN, bool TF32, bool OUT_F32, int ACT, bool TMA_OUT, int NGRP = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmO, uint8_t* stg, int grp, int lane,
                                               int m0, int nt0, uint32_t t_row) {
   constexpr int CH = OUT_F32 ? 32 : 64;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
   }
   if (rows_here > 0) {
 #pragma unroll 1
-    for (int c = grp; c < NCH; c += 2) {
+    for (int c = grp; c < NCH; c += NGRP) {
       const int n0 = nt0 + c * CH;
       if (n0 >= p.N) break;
       float v[CH];
@@ -254,7 +254,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         if (has_res) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
-          if (c + 2 < NCH && n0 + 2 * CH < p.N) load_res(n0 + 2 * CH);
+          if (c + NGRP < NCH && n0 + NGRP * CH < p.N) load_res(n0 + NGRP * CH);
         }
       }
       bias_act<CH, ACT, TF32, OUT_F32>(v, p.bias, n0, p.N, full);

@@ -210,3 +210,29 @@ def test_timm_dialect(golden_dir):
     _check(got, want)
     _check(got, torch.from_numpy(np.load(os.path.join(golden_dir, "timm_tiny_s5.npz"))["logits"]))
     _check(B200ViTForImageClassification.from_timm(tsd, precision="tf32")(x.cuda()).logits, want, tol=1e-3)
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at its full size (DeiT-Base, global batch 4096 as 4 chunks of 1024 -- the CTA-pair GEMMs at
+    M = 201 728 rows): images are independent units, so the logits of any image must not depend on what it is batched
+    with; a few images are also checked against the CPU oracle at the bf16 tolerance."""
+    from edgevisiontransformer_b200 import ops
+    spec = ViTSpec.deit("base")
+    sd = ovit.state_dict_of(ovit.build_hf_model(spec, seed=0, stress=True))
+    m = _model(sd, max_batch=1024, keep_params=False)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(4096, 3, 224, 224, device="cuda", generator=g)
+    big = m(x).logits
+    assert big.shape == (4096, 1000) and torch.isfinite(big).all()
+    pick = torch.tensor([0, 1, 1023, 1024, 2500, 4095], device="cuda")
+    try:
+        ops.set_gemm_split_k(False)
+        small = m(x[pick].contiguous()).logits          # same images, batch 6: small-M kernels (1-CTA GEMM, narrow tiles)
+    finally:
+        ops.set_gemm_split_k(True)
+    r = ovit.compare_logits(big[pick], small)
+    assert r["max_abs"] <= 5e-3 and r["top1_agree"] == 1.0, r
+    want = ovit.vit_forward(sd, spec, x[pick[:3]].cpu())
+    _check(big[pick[:3]], want)
+    # a second pass over the same inputs reproduces the first bit for bit (no split K at this size, fixed schedules)
+    assert torch.equal(m(x).logits, big)
