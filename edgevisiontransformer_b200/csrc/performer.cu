@@ -18,7 +18,6 @@ namespace {
 
 constexpr int kEmb = 64;
 constexpr int kM = 32;
-constexpr int kChunk = 196;  // tokens per reduce block
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -27,114 +26,245 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------- unfold (+ LN)
-// One warp per output row.  Row length L = k*k*C <= 32 * kMaxPerLane.
-constexpr int kMaxPerLane = 18;  // 576 / 32
+// One warp per output row; lane l owns the column pairs (64 i + 2 l, + 1), so stores are packed bf16x2 (128 B per warp
+// instruction).  KK / CC > 0 fix the window and channel count at compile time (T2T: 7 x 7 x 3 and 3 x 3 x 64) -- the
+// column -> (ky, kx, c) decomposition is then multiply-shift arithmetic instead of integer divisions by run-time values,
+// which is what the run-time-generic version (KK = 0) spent most of its instructions on (0.94 ms -> see DESIGN.md).
+// Row length L = k*k*C <= 64 * kMaxPairs.
+constexpr int kMaxPairs = 9;  // 576 / 64
 
-template <typename TIN, bool LN>
+template <typename TIN, bool LN, int KK, int CC>
 __global__ void __launch_bounds__(256) unfold_ln_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                         long long ldo, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int B, int H, int W,
-                                                        int C, int k, int s, int p, int oh, int ow, long long rows) {
+                                                        int C_rt, int k_rt, int s, int p, int oh, int ow, long long rows) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const int k = KK > 0 ? KK : k_rt;
+  const int C = CC > 0 ? CC : C_rt;
   const int L = k * k * C;
+  constexpr int NP = KK > 0 ? (KK * KK * CC + 63) / 64 : kMaxPairs;
   const int ox = static_cast<int>(row % ow);
   const int oy = static_cast<int>((row / ow) % oh);
   const long long b = row / (static_cast<long long>(ow) * oh);
   const int kC = k * C;
-  float v[kMaxPerLane];
+  const int ix0 = ox * s - p, iy0 = oy * s - p;
+  const TIN* xb = x + b * H * static_cast<long long>(W) * C;
+  auto fetch = [&](int col) -> float {
+    if (col >= L) return 0.f;
+    const int ky = col / kC;
+    const int rem = col - ky * kC;  // kx*C + c : contiguous in the input row
+    const int kx = rem / C;
+    const int iy = iy0 + ky, ix = ix0 + kx;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return 0.f;
+    return static_cast<float>(xb[(static_cast<long long>(iy) * W + ix0) * C + rem]);
+  };
+  float v0[NP], v1[NP];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int col = i * 32 + lane;
-    float val = 0.f;
-    if (col < L) {
-      const int ky = col / kC;
-      const int rem = col - ky * kC;  // kx*C + c : contiguous in the input row
-      const int kx = rem / C;
-      const int iy = oy * s - p + ky, ix = ox * s - p + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-        val = static_cast<float>(x[((b * H + iy) * W + ox * s - p) * C + rem]);
+  for (int i = 0; i < NP; ++i) {
+    const int col = i * 64 + 2 * lane;
+    if constexpr (CC > 0 && CC % 2 == 0 && sizeof(TIN) == 4) {
+      // both columns of the pair lie in the same (ky, kx) cell: one 8-byte load
+      float2 t = make_float2(0.f, 0.f);
+      if (col < L) {
+        const int ky = col / kC;
+        const int rem = col - ky * kC;
+        const int kx = rem / C;
+        const int iy = iy0 + ky, ix = ix0 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          t = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(xb) + (static_cast<long long>(iy) * W + ix0) * C + rem);
+      }
+      v0[i] = t.x;
+      v1[i] = t.y;
+    } else {
+      v0[i] = fetch(col);
+      v1[i] = fetch(col + 1);
     }
-    v[i] = val;
-    sum += val;
+    sum += v0[i] + v1[i];
   }
   float mean = 0.f, rstd = 1.f;
   if (LN) {
     mean = warp_sum(sum) / static_cast<float>(L);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
-      const int col = i * 32 + lane;
-      if (col < L) {
-        const float d = v[i] - mean;
-        q += d * d;
-      }
+    for (int i = 0; i < NP; ++i) {
+      const int col = i * 64 + 2 * lane;
+      const float d0 = v0[i] - mean, d1 = v1[i] - mean;
+      if (col < L) q += d0 * d0;
+      if (col + 1 < L) q += d1 * d1;
     }
     rstd = rsqrtf(warp_sum(q) / static_cast<float>(L) + eps);
   }
-  __nv_bfloat16* orow = out + row * ldo;
+  __nv_bfloat16* orow = out + row * ldo;  // ldo is even and the base 4-byte aligned (checked by the launcher)
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int col = i * 32 + lane;
+  for (int i = 0; i < NP; ++i) {
+    const int col = i * 64 + 2 * lane;
     if (col < ldo) {
-      float o = 0.f;
-      if (col < L) o = LN ? (v[i] - mean) * rstd * gamma[col] + beta[col] : v[i];
-      orow[col] = __float2bfloat16_rn(o);
+      float o0 = 0.f, o1 = 0.f;
+      if (col < L) o0 = LN ? (v0[i] - mean) * rstd * gamma[col] + beta[col] : v0[i];
+      if (col + 1 < L) o1 = LN ? (v1[i] - mean) * rstd * gamma[col + 1] + beta[col + 1] : v1[i];
+      *reinterpret_cast<__nv_bfloat162*>(orow + col) = __floats2bfloat162_rn(o0, o1);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- performer
-// prm_exp for one token held by a warp: lane m returns exp(w[m,:].x - |x|^2/2) / sqrt(32).
-// xa, xb = elements 2*lane, 2*lane+1 of the 64-vector; wreg = row `lane` of w.
-__device__ __forceinline__ float prm_exp_lane(const float (&wreg)[kEmb], float xa, float xb) {
-  float dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float a = __shfl_sync(0xffffffffu, xa, i);
-    const float b = __shfl_sync(0xffffffffu, xb, i);
-    dot = fmaf(wreg[2 * i], a, dot);
-    dot = fmaf(wreg[2 * i + 1], b, dot);
-  }
-  const float xd = 0.5f * warp_sum(xa * xa + xb * xb);
-  return __expf(dot - xd) * 0.17677669529663687f;  // 1/sqrt(32)
+// Both kernels are chains of small matrix products per 16-token tile and run them on the warp-level tensor path
+// (mma.sync m16n8k16, bf16 operands, f32 accumulate) -- the first version walked them with 128 warp shuffles per token
+// and was shuffle-issue bound (0.61 + 0.94 ms for 802 816 tokens; now HBM-bound).  Orientation is chosen so that every
+// accumulator fragment is directly the A fragment of the next product (no transposes through shared memory except V):
+//   reduce : WTX^T[32 x 16] = W[32 x 64] K^T[64 x 16]  ->  kp^T = exp(WTX^T - |k|^2/2)/sqrt(32)
+//            kptv^T[32 x 64] += kp^T[32 x 16] V[16 x 64]       (V via ldmatrix.trans from a swizzled 2 KB tile)
+//   apply  : WTX[16 x 32] = Q[16 x 64] W^T[64 x 32]     ->  qp = exp(WTX - |q|^2/2)/sqrt(32)
+//            Y[16 x 64] = qp[16 x 32] kptv^T[32 x 64];  D = qp . ksum (f32)
+// The random-feature matrix w enters as a bf16 hi + lo pair (two MMAs), i.e. with 16 mantissa bits: rounding w itself to
+// bf16 would shift every exponent by up to ~0.02.  k, q, v are bf16 already; kp / qp / kptv are rounded to bf16 only as
+// tensor-core operands (like P in attention) while ksum and D stay f32.
+constexpr int kTileTok = 16;
+constexpr int kChunk = 256;  // tokens per block: 4 warps x 4 tiles
+constexpr float kInvSqrtM = 0.17677669529663687f;  // 1/sqrt(32)
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// (hi, lo) bf16 pairs of two consecutive f32 values: x ~= hi + lo with 16 mantissa bits
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  hi = pack2(__bfloat162float(ha), __bfloat162float(hb));
+  lo = pack2(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+__device__ __forceinline__ float sumsq_bf16x2(uint32_t v) {
+  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  return f.x * f.x + f.y * f.y;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
 }
 
 // kqv: bf16 [B*T, ld] with k at cols [0,64), q at [64,128), v at [128,192).
-// partial: f32 [B, nsplit, 32 + 64*32]  (ksum | kptv[n][m])
+// partial: f32 [B, nsplit, 32 + 64*32]  (ksum[m] | kptv[n][m])
 __global__ void __launch_bounds__(128) performer_reduce_kernel(const __nv_bfloat16* __restrict__ kqv, long long ld,
                                                                const float* __restrict__ w, float* __restrict__ partial,
                                                                int T, int nsplit) {
   __shared__ float red[4][kM + kEmb * kM];
+  __shared__ __align__(128) uint8_t vtile[4][kTileTok * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int split = blockIdx.x, b = blockIdx.y;
-  float wreg[kEmb];
+  // A fragments of W[32 features x 64]: m-tile mi, k-step ks
+  uint32_t whi[2][4][4], wlo[2][4][4];
 #pragma unroll
-  for (int i = 0; i < kEmb; ++i) wreg[i] = w[lane * kEmb + i];
-  float ksum = 0.f;
-  float acc[kEmb];  // kptv[n][lane]
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-  for (int n = 0; n < kEmb; ++n) acc[n] = 0.f;
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 x = *reinterpret_cast<const float2*>(w + (mi * 16 + g + (r & 1) * 8) * kEmb + ks * 16 + (r >> 1) * 8 + 2 * t);
+        split2(x.x, x.y, whi[mi][ks][r], wlo[mi][ks][r]);
+      }
+  float ksum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // features mi*16 + g, mi*16 + g + 8 (summed over this lane's token columns)
+  float kacc[2][8][4];                           // kptv^T: (feature mi*16 + g (+8), emb ne*8 + 2t (+1))
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ne = 0; ne < 8; ++ne) kacc[mi][ne][0] = kacc[mi][ne][1] = kacc[mi][ne][2] = kacc[mi][ne][3] = 0.f;
   const int t0 = split * kChunk, t1 = min(T, t0 + kChunk);
-  for (int t = t0 + warp; t < t1; t += 4) {
-    const __nv_bfloat16* rowp = kqv + (static_cast<long long>(b) * T + t) * ld;
-    const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rowp + 2 * lane));
-    const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rowp + 128 + 2 * lane));
-    const float kp = prm_exp_lane(wreg, kk.x, kk.y);
-    ksum += kp;
+  const uint32_t vt = ptx::smem_u32(vtile[warp]);
+  for (int tb = t0 + warp * kTileTok; tb < t1; tb += 4 * kTileTok) {
+    const __nv_bfloat16* base = kqv + (static_cast<long long>(b) * T + tb) * ld;
+    // V tile -> shared memory (16 rows x 128 B, 16-byte chunks XOR-swizzled by row & 7); rows past t1 are zero
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float va = __shfl_sync(0xffffffffu, vv.x, i);
-      const float vb = __shfl_sync(0xffffffffu, vv.y, i);
-      acc[2 * i] = fmaf(va, kp, acc[2 * i]);
-      acc[2 * i + 1] = fmaf(vb, kp, acc[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i, row = c >> 3, ch = c & 7;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (tb + row < t1) val = *reinterpret_cast<const uint4*>(base + row * ld + 128 + ch * 8);
+      *reinterpret_cast<uint4*>(vtile[warp] + row * 128 + ((ch ^ (row & 7)) << 4)) = val;
+    }
+    // K fragments (B operand, n = token): n-tile nj = tokens 8 nj + g
+    uint32_t kb[2][4][2];
+    float xd[2];
+#pragma unroll
+    for (int nj = 0; nj < 2; ++nj) {
+      const bool ok = tb + nj * 8 + g < t1;
+      const __nv_bfloat16* rp = base + (nj * 8 + g) * ld + 2 * t;
+      float sq = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        kb[nj][ks][0] = ok ? *reinterpret_cast<const uint32_t*>(rp + ks * 16) : 0u;
+        kb[nj][ks][1] = ok ? *reinterpret_cast<const uint32_t*>(rp + ks * 16 + 8) : 0u;
+        sq += sumsq_bf16x2(kb[nj][ks][0]) + sumsq_bf16x2(kb[nj][ks][1]);
+      }
+      xd[nj] = 0.5f * quad_sum(sq);  // |k|^2 / 2 of token 8 nj + g, in all four lanes of the quad
+    }
+    __syncwarp();
+    uint32_t pa[2][4];  // kp^T as A fragments (features x 16 tokens)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+      for (int nj = 0; nj < 2; ++nj) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_bf16(acc, whi[mi][ks], kb[nj][ks][0], kb[nj][ks][1]);
+          mma_bf16(acc, wlo[mi][ks], kb[nj][ks][0], kb[nj][ks][1]);
+        }
+        // columns of this lane: tokens 8 nj + 2t, + 1
+        const float x0 = __shfl_sync(0xffffffffu, xd[nj], (2 * t) * 4);
+        const float x1 = __shfl_sync(0xffffffffu, xd[nj], (2 * t + 1) * 4);
+        const bool ok0 = tb + nj * 8 + 2 * t < t1, ok1 = tb + nj * 8 + 2 * t + 1 < t1;
+        const float p0 = ok0 ? __expf(acc[0] - x0) * kInvSqrtM : 0.f;
+        const float p1 = ok1 ? __expf(acc[1] - x1) * kInvSqrtM : 0.f;
+        const float p2 = ok0 ? __expf(acc[2] - x0) * kInvSqrtM : 0.f;
+        const float p3 = ok1 ? __expf(acc[3] - x1) * kInvSqrtM : 0.f;
+        ksum[mi][0] += p0 + p1;
+        ksum[mi][1] += p2 + p3;
+        pa[mi][nj * 2] = pack2(p0, p1);
+        pa[mi][nj * 2 + 1] = pack2(p2, p3);
+      }
+    }
+    // kptv^T += kp^T V
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t vb[4];  // {b0, b1} of emb n-tile 2 np, {b0, b1} of 2 np + 1
+      const int row = (lane & 7) + ((lane >> 3) & 1) * 8, ch = np * 2 + (lane >> 4);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
+                   : "r"(vt + row * 128 + ((ch ^ (row & 7)) << 4)));
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16(kacc[mi][2 * np], pa[mi], vb[0], vb[1]);
+        mma_bf16(kacc[mi][2 * np + 1], pa[mi], vb[2], vb[3]);
+      }
     }
   }
-  red[warp][lane] = ksum;
+  // per-warp results -> shared memory in the [ksum | kptv[n][m]] layout, then a fixed-order sum over the four warps
 #pragma unroll
-  for (int n = 0; n < kEmb; ++n) red[warp][kM + n * kM + lane] = acc[n];
+  for (int mi = 0; mi < 2; ++mi) {
+    const float s0 = quad_sum(ksum[mi][0]), s1 = quad_sum(ksum[mi][1]);
+    if (t == 0) {
+      red[warp][mi * 16 + g] = s0;
+      red[warp][mi * 16 + g + 8] = s1;
+    }
+#pragma unroll
+    for (int ne = 0; ne < 8; ++ne) {
+      const int n = ne * 8 + 2 * t, m = mi * 16 + g;
+      red[warp][kM + n * kM + m] = kacc[mi][ne][0];
+      red[warp][kM + (n + 1) * kM + m] = kacc[mi][ne][1];
+      red[warp][kM + n * kM + m + 8] = kacc[mi][ne][2];
+      red[warp][kM + (n + 1) * kM + m + 8] = kacc[mi][ne][3];
+    }
+  }
   __syncthreads();
   float* dst = partial + (static_cast<long long>(b) * nsplit + split) * (kM + kEmb * kM);
   for (int i = threadIdx.x; i < kM + kEmb * kM; i += 128) dst[i] = ((red[0][i] + red[1][i]) + red[2][i]) + red[3][i];
@@ -158,41 +288,105 @@ __global__ void __launch_bounds__(128) performer_apply_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ yattn, float* __restrict__ vout,
                                                               int T, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.y;
   const float* st = stats + static_cast<long long>(b) * (kM + kEmb * kM);
-  float wreg[kEmb];
+  // B fragments of W^T[64 emb x 32 features]: n-tile nf = features 8 nf + g, k-step ks
+  uint32_t whi[4][4][2], wlo[4][4][2];
 #pragma unroll
-  for (int i = 0; i < kEmb; ++i) wreg[i] = w[lane * kEmb + i];
-  const float ksum = st[lane];
-  float kv0[kM], kv1[kM];  // kptv[lane][m], kptv[lane+32][m]
+  for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
-  for (int m = 0; m < kM; ++m) {
-    kv0[m] = st[kM + lane * kM + m];
-    kv1[m] = st[kM + (lane + 32) * kM + m];
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float2 x = *reinterpret_cast<const float2*>(w + (nf * 8 + g) * kEmb + ks * 16 + r * 8 + 2 * t);
+        split2(x.x, x.y, whi[nf][ks][r], wlo[nf][ks][r]);
+      }
+  // B fragments of kptv^T[32 features x 64 emb]: n-tile ne = emb 8 ne + g, k-step ks = features 16 ks ..
+  uint32_t kvb[8][2][2];
+#pragma unroll
+  for (int ne = 0; ne < 8; ++ne)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float2 x = *reinterpret_cast<const float2*>(st + kM + (ne * 8 + g) * kM + ks * 16 + r * 8 + 2 * t);
+        kvb[ne][ks][r] = pack2(x.x, x.y);
+      }
+  float ksm[4][2];  // ksum of this lane's feature columns 8 nf + 2t, + 1
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) {
+    ksm[nf][0] = st[nf * 8 + 2 * t];
+    ksm[nf][1] = st[nf * 8 + 2 * t + 1];
   }
   const int t0 = blockIdx.x * kChunk, t1 = min(T, t0 + kChunk);
-  for (int t = t0 + warp; t < t1; t += 4) {
-    const long long r = static_cast<long long>(b) * T + t;
-    const __nv_bfloat16* rowp = kqv + r * ld;
-    const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rowp + 64 + 2 * lane));
-    const float qp = prm_exp_lane(wreg, qq.x, qq.y);
-    const float D = warp_sum(qp * ksum);
-    float y0 = 0.f, y1 = 0.f;
+  for (int tb = t0 + warp * kTileTok; tb < t1; tb += 4 * kTileTok) {
+    const long long r0 = static_cast<long long>(b) * T + tb;
+    const __nv_bfloat16* base = kqv + r0 * ld;
+    const bool okA = tb + g < t1, okB = tb + g + 8 < t1;  // rows g and g + 8 of the tile
+    // Q fragments (A operand): rows = tokens g, g + 8
+    uint32_t qa[4][4];
+    float sqA = 0.f, sqB = 0.f;
 #pragma unroll
-    for (int m = 0; m < kM; ++m) {
-      const float qm = __shfl_sync(0xffffffffu, qp, m);
-      y0 = fmaf(qm, kv0[m], y0);
-      y1 = fmaf(qm, kv1[m], y1);
+    for (int ks = 0; ks < 4; ++ks) {
+      const __nv_bfloat16* ra = base + g * ld + 64 + ks * 16 + 2 * t;
+      const __nv_bfloat16* rb = ra + 8 * ld;
+      qa[ks][0] = okA ? *reinterpret_cast<const uint32_t*>(ra) : 0u;
+      qa[ks][1] = okB ? *reinterpret_cast<const uint32_t*>(rb) : 0u;
+      qa[ks][2] = okA ? *reinterpret_cast<const uint32_t*>(ra + 8) : 0u;
+      qa[ks][3] = okB ? *reinterpret_cast<const uint32_t*>(rb + 8) : 0u;
+      sqA += sumsq_bf16x2(qa[ks][0]) + sumsq_bf16x2(qa[ks][2]);
+      sqB += sumsq_bf16x2(qa[ks][1]) + sumsq_bf16x2(qa[ks][3]);
     }
-    const float inv = 1.0f / (D + eps);
-    yattn[r * kEmb + lane] = __float2bfloat16_rn(y0 * inv);
-    yattn[r * kEmb + lane + 32] = __float2bfloat16_rn(y1 * inv);
-    vout[r * kEmb + lane] = __bfloat162float(rowp[128 + lane]);
-    vout[r * kEmb + lane + 32] = __bfloat162float(rowp[128 + lane + 32]);
+    const float xA = 0.5f * quad_sum(sqA), xB = 0.5f * quad_sum(sqB);
+    uint32_t pa[2][4];  // qp as A fragments of the two k-steps (features 0..15, 16..31)
+    float dA = 0.f, dB = 0.f;
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        mma_bf16(acc, qa[ks], whi[nf][ks][0], whi[nf][ks][1]);
+        mma_bf16(acc, qa[ks], wlo[nf][ks][0], wlo[nf][ks][1]);
+      }
+      const float p0 = __expf(acc[0] - xA) * kInvSqrtM, p1 = __expf(acc[1] - xA) * kInvSqrtM;
+      const float p2 = __expf(acc[2] - xB) * kInvSqrtM, p3 = __expf(acc[3] - xB) * kInvSqrtM;
+      dA = fmaf(p0, ksm[nf][0], fmaf(p1, ksm[nf][1], dA));
+      dB = fmaf(p2, ksm[nf][0], fmaf(p3, ksm[nf][1], dB));
+      pa[nf >> 1][(nf & 1) * 2] = pack2(p0, p1);
+      pa[nf >> 1][(nf & 1) * 2 + 1] = pack2(p2, p3);
+    }
+    const float invA = 1.0f / (quad_sum(dA) + eps), invB = 1.0f / (quad_sum(dB) + eps);
+#pragma unroll
+    for (int ne = 0; ne < 8; ++ne) {
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16(y, pa[0], kvb[ne][0][0], kvb[ne][0][1]);
+      mma_bf16(y, pa[1], kvb[ne][1][0], kvb[ne][1][1]);
+      const int col = ne * 8 + 2 * t;
+      if (okA) *reinterpret_cast<uint32_t*>(yattn + (r0 + g) * kEmb + col) = pack2(y[0] * invA, y[1] * invA);
+      if (okB) *reinterpret_cast<uint32_t*>(yattn + (r0 + g + 8) * kEmb + col) = pack2(y[2] * invB, y[3] * invB);
+    }
+    // vout = v as f32: 16 rows x 32 bf16 pairs, coalesced
+#pragma unroll
+    for (int i = 0; i < kTileTok; ++i) {
+      if (tb + i < t1) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + i * ld + 128 + 2 * lane));
+        *reinterpret_cast<float2*>(vout + (r0 + i) * kEmb + 2 * lane) = f;
+      }
+    }
   }
 }
 
 }  // namespace
+
+template <typename TIN, bool LN>
+void unfold_ln_dispatch(const TIN* xi, __nv_bfloat16* o, int64_t ldo, const float* gamma, const float* beta, float eps, int B, int H,
+                        int W, int C, int k, int s, int p, int oh, int ow, long long rows, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (k == 7 && C == 3) unfold_ln_kernel<TIN, LN, 7, 3><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+  else if (k == 3 && C == 64) unfold_ln_kernel<TIN, LN, 3, 64><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+  else unfold_ln_kernel<TIN, LN, 0, 0><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+}
 
 int unfold_ln_launch(const void* x, int x_dtype, void* out, int64_t ldo, const float* gamma, const float* beta, float eps,
                      int B, int H, int W, int C, int k, int s, int p, cudaStream_t st) {
@@ -200,22 +394,23 @@ int unfold_ln_launch(const void* x, int x_dtype, void* out, int64_t ldo, const f
   EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && k > 0 && s > 0 && p >= 0, "unfold_ln: bad sizes");
   const int L = k * k * C;
   EVT_CHECK_ARG(ldo >= L, "unfold_ln: ldo smaller than k*k*C");
-  if (ldo > 32 * kMaxPerLane) return fail(EVT_ERR_UNSUPPORTED, "unfold_ln: rows longer than 576 elements are not implemented");
+  EVT_CHECK_ARG(ldo % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0, "unfold_ln: ldo must be even and out 4-byte aligned");
+  if (ldo > 64 * kMaxPairs) return fail(EVT_ERR_UNSUPPORTED, "unfold_ln: rows longer than 576 elements are not implemented");
   EVT_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "unfold_ln: gamma and beta must both be given or both be null");
   const int oh = (H + 2 * p - k) / s + 1, ow = (W + 2 * p - k) / s + 1;
   EVT_CHECK_ARG(oh > 0 && ow > 0, "unfold_ln: empty output");
   const long long rows = static_cast<long long>(B) * oh * ow;
-  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   const bool ln = gamma != nullptr;
   if (x_dtype == EVT_F32) {
     const float* xi = reinterpret_cast<const float*>(x);
-    if (ln) unfold_ln_kernel<float, true><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
-    else unfold_ln_kernel<float, false><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+    EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 8 == 0, "unfold_ln: x must be 8-byte aligned");
+    if (ln) unfold_ln_dispatch<float, true>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows, st);
+    else unfold_ln_dispatch<float, false>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows, st);
   } else if (x_dtype == EVT_BF16) {
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
-    if (ln) unfold_ln_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
-    else unfold_ln_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+    if (ln) unfold_ln_dispatch<__nv_bfloat16, true>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows, st);
+    else unfold_ln_dispatch<__nv_bfloat16, false>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows, st);
   } else {
     return fail(EVT_ERR_INVALID, "unfold_ln: x dtype must be f32 or bf16");
   }
@@ -249,7 +444,11 @@ extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, vo
   EVT_CHECK_ARG(kqv && w && yattn && vout && workspace, "performer: null pointer");
   EVT_CHECK_ARG(B > 0 && T > 0 && B <= 65535, "performer: B in 1..65535 and T > 0");
   if (emb != kEmb || m != kM) return fail(EVT_ERR_UNSUPPORTED, "performer: only emb = 64, m = 32 (T2T token_size 64, kernel_ratio 0.5) is implemented");
-  EVT_CHECK_ARG(ld >= 3 * kEmb && ld % 2 == 0, "performer: kqv leading dimension must be >= 192 and even");
+  EVT_CHECK_ARG(ld >= 3 * kEmb && ld % 8 == 0 && reinterpret_cast<uintptr_t>(kqv) % 16 == 0,
+                "performer: kqv rows must be 16-byte aligned with a leading dimension >= 192");
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(w) % 8 == 0 && reinterpret_cast<uintptr_t>(workspace) % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(yattn) % 4 == 0 && reinterpret_cast<uintptr_t>(vout) % 8 == 0,
+                "performer: w / workspace / outputs must be 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nsplit = (T + kChunk - 1) / kChunk;
   float* partial = reinterpret_cast<float*>(workspace);
