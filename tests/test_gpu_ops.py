@@ -289,3 +289,25 @@ def test_errors_are_loud():
     a = torch.zeros((4, 12), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(ValueError):
         ops.linear(a[:, :9], a[:, :9], None)           # 24-byte rows: not a legal TMA leading dimension -> EVT_ERR_INVALID
+
+
+@pytest.mark.parametrize("B,T", [(2, 784), (3, 50), (1, 3136), (2, 257)])
+def test_performer_core_matches_restatement(B, T):
+    """evt_performer_fwd (TokenPerformer.single_attn core, transformer_encoder.py:67-94) against oracle.t2t.prm_exp; T values
+    cover partial 16-token tiles and partial 256-token blocks."""
+    import math
+    from edgevisiontransformer_b200 import ops
+    from oracle import t2t as ot2t
+    g = torch.Generator().manual_seed(T)
+    kqv = (torch.randn(B * T, 192, generator=g) * 0.7).bfloat16()
+    q_, _ = torch.linalg.qr(torch.randn(64, 32, generator=g))
+    w = (q_.t() * math.sqrt(32)).contiguous()
+    k, q, v = [t.float().view(B, T, 64) for t in kqv.split(64, dim=1)]
+    kp, qp = ot2t.prm_exp(k, w), ot2t.prm_exp(q, w)
+    D = torch.einsum("bti,bi->bt", qp, kp.sum(dim=1)).unsqueeze(2)
+    want = torch.einsum("bti,bni->btn", qp, torch.einsum("bin,bim->bnm", v, kp)) / (D + 1e-8)
+    yattn, vout = ops.performer(kqv.cuda(), w.cuda(), B, T)
+    assert torch.equal(vout.cpu(), v.reshape(B * T, 64))                      # the skip input is an exact copy
+    err = (yattn.float().cpu().view(B, T, 64) - want).abs().max().item()
+    assert err < 2e-2 * max(1.0, want.abs().max().item()), err                # bf16 operands / output
+    assert (yattn.float().cpu().view(B, T, 64) - want).abs().mean().item() < 2e-3
