@@ -16,8 +16,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // One thread = 8 consecutive pixels of one image row (32 B in, 16 B out).  Thread order follows the
 // input (b, c, y, x8) so reads are perfectly coalesced; writes are full 16-byte pieces of patch rows.
+// Patch p of image b lands in row  b * row_stride + row_off + p  (row_stride = patches, row_off = 0: dense patch matrix;
+// row_stride = tokens, row_off = number of prefix tokens: one row per TOKEN, so the embedding GEMM's output rows are the
+// rows of the residual stream and its epilogue can be the TMA reduce-add).
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ cols,
-                                                     int B, int H, int W, int P, long long total) {
+                                                     int B, int H, int W, int P, long long total, int row_stride, int row_off) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -33,8 +36,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ p
   const float4 v1 = *reinterpret_cast<const float4*>(px + t * 8 + 4);
   const int x = x8 * 8;
   const int py = y / P, i = y % P, pxi = x / P, j = x % P;
-  const int gw = W / P, gh = H / P;
-  const long long row = (static_cast<long long>(b) * gh + py) * gw + pxi;
+  const int gw = W / P;
+  const long long row = static_cast<long long>(b) * row_stride + row_off + py * gw + pxi;
   const int k = (c * P + i) * P + j;
   uint4 o;
   o.x = pack_bf16(v0.x, v0.y);
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ p
 
 // Same gather, f32 output (tf32 mode keeps the patch matrix in fp32).
 __global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict__ px, float* __restrict__ cols, int B,
-                                                         int H, int W, int P, long long total) {
+                                                         int H, int W, int P, long long total, int row_stride, int row_off) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -61,8 +64,8 @@ __global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict
   const float4 v = *reinterpret_cast<const float4*>(px + t * 4);
   const int x = x4 * 4;
   const int py = y / P, i = y % P, pxi = x / P, j = x % P;
-  const int gw = W / P, gh = H / P;
-  const long long row = (static_cast<long long>(b) * gh + py) * gw + pxi;
+  const int gw = W / P;
+  const long long row = static_cast<long long>(b) * row_stride + row_off + py * gw + pxi;
   const int k = (c * P + i) * P + j;
   *reinterpret_cast<float4*>(cols + row * (3ll * P * P) + k) =
       make_float4(ptx::round_tf32(v.x), ptx::round_tf32(v.y), ptx::round_tf32(v.z), ptx::round_tf32(v.w));
@@ -80,6 +83,23 @@ __global__ void __launch_bounds__(256) prefix_tokens_kernel(const float* __restr
   const int tk = static_cast<int>((t / D) % n_prefix);
   const long long b = t / (static_cast<long long>(D) * n_prefix);
   out[(b * tokens + tk) * D + d] = prefix[tk * D + d] + pos[tk * D + d];
+}
+
+// Residual stream before the embedding GEMM reduce-adds the patch projections into it:
+//   out[b, t, :] = pos[t, :] + (t < n_prefix ? prefix[t, :] : bias[:])     (cls / distillation rows; conv bias elsewhere)
+__global__ void __launch_bounds__(256) embed_fill_kernel(const float* __restrict__ prefix, const float* __restrict__ pos,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         long long total4, int tokens, int n_prefix, int D4) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int d4 = static_cast<int>(i % D4);
+  const int tk = static_cast<int>((i / D4) % tokens);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<long long>(tk) * D4 + d4);
+  const float4 c = tk < n_prefix ? __ldg(reinterpret_cast<const float4*>(prefix) + static_cast<long long>(tk) * D4 + d4)
+                                 : __ldg(reinterpret_cast<const float4*>(bias) + d4);
+  reinterpret_cast<float4*>(out)[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
 }
 
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -128,24 +148,37 @@ __global__ void __launch_bounds__(256) unfold_kernel(const TIN* __restrict__ x, 
 
 }  // namespace
 
-int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st) {
+int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st, int row_stride,
+                  int row_off) {
+  if (row_stride <= 0) row_stride = (H / (P > 0 ? P : 1)) * (W / (P > 0 ? P : 1)), row_off = 0;
   EVT_CHECK_ARG(pixels && cols, "im2col: null pointer");
   EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && P > 0, "im2col: sizes must be positive");
   EVT_CHECK_ARG(H % P == 0 && W % P == 0, "im2col: image size must be a multiple of the patch size");
   EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(pixels) % 16 == 0 && reinterpret_cast<uintptr_t>(cols) % 16 == 0,
                 "im2col: pointers must be 16-byte aligned");
-  if (P % 8 != 0 && P % 4 == 0 && out_dtype == EVT_BF16) return im2col4_launch(pixels, cols, B, H, W, P, st);  // Swin: P = 4
+  if (P % 8 != 0 && P % 4 == 0 && out_dtype == EVT_BF16 && row_off == 0) return im2col4_launch(pixels, cols, B, H, W, P, st);  // Swin: P = 4
   EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8 (bf16: of 4)");
   if (out_dtype == EVT_BF16) {
     const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
     EVT_CUDA(launch_pdl(im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
-                        reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total));
+                        reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total, row_stride, row_off));
   } else {
     const long long total = static_cast<long long>(B) * 3 * H * (W / 4);
     EVT_CUDA(launch_pdl(im2col_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
-                        reinterpret_cast<float*>(cols), B, H, W, P, total));
+                        reinterpret_cast<float*>(cols), B, H, W, P, total, row_stride, row_off));
   }
   EVT_LAUNCH_CHECK("im2col");
+  return EVT_OK;
+}
+
+int embed_fill_launch(const float* prefix, const float* pos, const float* bias, float* out, int B, int tokens, int n_prefix, int D,
+                      cudaStream_t st) {
+  EVT_CHECK_ARG(prefix && pos && bias && out, "embed_fill: null pointer");
+  EVT_CHECK_ARG(B > 0 && tokens > 0 && n_prefix > 0 && n_prefix <= tokens && D > 0 && D % 4 == 0, "embed_fill: bad sizes");
+  const long long total4 = static_cast<long long>(B) * tokens * (D / 4);
+  EVT_CUDA(launch_pdl(embed_fill_kernel, dim3(static_cast<unsigned>((total4 + 255) / 256)), dim3(256), 0, st,
+                      pdl_for_rows(static_cast<long long>(B) * tokens), prefix, pos, bias, out, total4, tokens, n_prefix, D / 4));
+  EVT_LAUNCH_CHECK("embed_fill");
   return EVT_OK;
 }
 

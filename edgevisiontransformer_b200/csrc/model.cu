@@ -116,7 +116,8 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   const size_t o_xn = take(M * s.hidden * es);
   const size_t o_qkv = take(M * 3 * amax * es);
   const size_t o_ctx = take(M * amax * es);
-  const size_t o_big = take(std::max(M * imax_ld, Mp * static_cast<size_t>(m->patch_k)) * es);
+  // the patch matrix has one row per TOKEN when the library builds it (pixels path), see forward_impl
+  const size_t o_big = take(std::max(M * imax_ld, (s.embed_k > 0 ? Mp : M) * static_cast<size_t>(m->patch_k)) * es);
   const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * es);
   const size_t o_hh = take(static_cast<size_t>(batch) * std::max(padn(s.head_hidden, m->pad), 8) * es);
   w.resid = reinterpret_cast<float*>(b + o_resid);
@@ -353,7 +354,7 @@ extern "C" int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* 
 extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   if (!m) return 0;
   const evt_model_spec& s = m->spec;
-  return 3 + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+  return (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
 static int forward_impl(evt_model* m, const float* pixels, const void* patch_matrix, int64_t patch_ld, int batch,
@@ -402,19 +403,25 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   const int dt = tf32 ? EVT_F32 : EVT_BF16;   // GEMM operand type
   const int adt = tf32 ? EVT_TF32 : EVT_BF16;  // type activations are WRITTEN in (tf32: f32 storage, rounded to nearest)
   // embeddings
-  const void* pm = patch_matrix;
-  int64_t pm_ld = patch_ld;
-  if (pm == nullptr) {
+  if (patch_matrix == nullptr) {
+    // Pixels path: the patch matrix gets one row per token (prefix rows zero), so the embedding GEMM is a plain
+    // M = batch * tokens problem whose output rows ARE the residual rows -> CTA-pair kernel + TMA reduce-add epilogue.
+    // The residual stream is first filled with pos + (cls | conv bias); the GEMM then adds the patch projections.
+    // (Before: remapped output rows forced the generic epilogue -- 1.0 ms of a 41 ms forward at batch 1024, now 0.4.)
     EVT_CHECK_ARG(s.embed_k == 0, "this model takes a caller-built patch matrix (evt_model_forward_embedded)");
-    EVT_STAGE(EVT_STAGE_EMBED, im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st));
-    pm = w.big;
-    pm_ld = m->patch_k;
+    const size_t row_bytes = static_cast<size_t>(m->patch_k) * m->es;
+    EVT_CUDA(cudaMemset2DAsync(w.big, s.tokens * row_bytes, 0, m->n_prefix * row_bytes, batch, st));
+    EVT_STAGE(EVT_STAGE_EMBED, im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st, s.tokens, m->n_prefix));
+    EVT_STAGE(EVT_STAGE_EMBED, embed_fill_launch(m->prefix, m->pos, m->b_patch, w.resid, batch, s.tokens, m->n_prefix, D, st));
+    EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, dt, nullptr, w.resid, D, 0, 0, w.resid, EVT_F32, D,
+                                           0, 0, 0, M, D, m->patch_k, EVT_ACT_NONE, st));
   } else {
-    EVT_CHECK_ARG(pm_ld >= m->patch_k, "patch matrix leading dimension smaller than the embedding K");
+    EVT_CHECK_ARG(patch_ld >= m->patch_k, "patch matrix leading dimension smaller than the embedding K");
+    EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(patch_matrix, patch_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches,
+                                           m->n_prefix, w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k,
+                                           EVT_ACT_NONE, st));
+    EVT_STAGE(EVT_STAGE_EMBED, prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
   }
-  EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(pm, pm_ld, m->w_patch, m->patch_k, dt, m->b_patch, m->pos, D, m->patches, m->n_prefix,
-                      w.resid, EVT_F32, D, m->patches, s.tokens, m->n_prefix, Mp, D, m->patch_k, EVT_ACT_NONE, st));
-  EVT_STAGE(EVT_STAGE_EMBED, prefix_tokens_launch(m->prefix, m->pos, w.resid, batch, s.tokens, m->n_prefix, D, st));
   // encoder.  EXPERIMENTAL (EVT_FUSE_LN=1, off by default): with bf16 operands and the HF dataflow the LayerNorm that
   // FOLLOWS each residual projection can run inside that GEMM's epilogue (gemm3.cu).  It is bit-identical on the residual
   // stream but measured SLOWER on B200 (0.42 vs 0.22 ms for out-proj + LN at 100k rows): the second pass over the new
