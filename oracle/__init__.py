@@ -24,6 +24,11 @@ the installed ``transformers`` package whose arithmetic the reference calls):
                       ``modeling/layers/*``).
 * ``oracle.t2t``      T2T-ViT (``modeling/models/t2t_vit.py:7-148``,
                       ``modeling/layers/transformer_encoder.py:39-101``).
+* ``oracle.timm_vit`` timm / facebookresearch-deit ``VisionTransformer`` (the model
+                      ``utils.py:52-62`` loads over torch.hub; not under /root/reference).
+* ``oracle.swin``     Swin Transformer classifier (the model ``utils.py:14-47`` builds from
+                      an external microsoft/Swin-Transformer checkout; arithmetic as in
+                      ``SITE/models/swin/modeling_swin.py``).
 
 Pinning status
 --------------
@@ -37,6 +42,9 @@ script ``tests/golden/make_golden.py``:
   from /root/reference (fixtures ``hf_*.npz``, ``pruned_*.npz``).
 * ``oracle.torch_layers``  pinned against ``/root/reference/modeling/torch_layers``
   imported unchanged (fixtures ``torch_layers_*.npz``).
+* ``oracle.timm_vit`` / ``oracle.swin``  pinned against the installed ``transformers``
+  implementations of the same networks (fixtures ``timm_tiny_s5.npz``, ``swin_tiny_*.npz``);
+  unpinned against timm / the microsoft repository themselves (external, not fetchable).
 * ``oracle.tf_vit`` / ``oracle.t2t``  **parity unpinned**: TensorFlow is not
   installed, the reference's implementation cannot run here, and the
   reference ships no fixture for it.  They are line-by-line restatements only.
