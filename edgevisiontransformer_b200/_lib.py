@@ -11,7 +11,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libevt.so")
+LIB_PATH = os.environ.get("EVT_LIB_PATH") or os.path.join(HERE, "libevt.so")   # EVT_LIB_PATH: A/B a differently built library
 
 EVT_OK, EVT_ERR_INVALID, EVT_ERR_CUDA, EVT_ERR_UNSUPPORTED, EVT_ERR_STATE = 0, -1, -2, -3, -4
 EVT_F32, EVT_BF16 = 0, 1

@@ -35,6 +35,12 @@ constexpr int kThreadsP = 32 * (kSoftmaxWarps + 2);
 constexpr int kSlotCols = 256;
 constexpr int kOCol = 128;
 constexpr int kMaxStages = 4;
+#ifndef EVT_ATTN_POLY_PAIRS
+#define EVT_ATTN_POLY_PAIRS 1
+#endif
+// Of every 4 pairs of exponentials, how many run on the FMA pipe (0..4).  Measured at B = 1024, S = 197, 12 heads on one box:
+// 0 -> 0.319 ms, 1 -> 0.309, 2 -> 0.318, 3 -> 0.342 (0.330 before the division-free item bookkeeping).
+constexpr int kPolyPairs = EVT_ATTN_POLY_PAIRS;
 
 struct AttnParams {
   __nv_bfloat16* ctx;
@@ -73,6 +79,24 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// 2^t for t <= 0 on the FMA / ALU pipes (no MUFU): t = n + f with n = round(t) taken from the low mantissa bits of
+// t + 1.5 * 2^23 and f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16
+// rounding of P) and n added into the exponent field.  Used for one element pair in four: the exponential phase of the
+// two softmax groups is MUFU-bound whenever they overlap (ncu: mio-throttle stalls on MUFU.EX2), the FMA pipe is idle.
+__device__ __forceinline__ void ex2_poly_pair(float t0, float t1, float& p0, float& p1) {
+  const uint64_t tt = pk2(fmaxf(t0, -126.f), fmaxf(t1, -126.f));
+  const uint64_t r = add2(tt, pk2(12582912.f, 12582912.f));
+  const uint64_t f = add2(tt, fma2(r, pk2(-1.f, -1.f), pk2(12582912.f, 12582912.f)));  // t - n
+  uint64_t q = fma2(f, pk2(0.0551716685f, 0.0551716685f), pk2(0.2426111251f, 0.2426111251f));
+  q = fma2(q, f, pk2(0.6932609677f, 0.6932609677f));
+  q = fma2(q, f, pk2(0.9999280572f, 0.9999280572f));
+  float q0, q1, r0, r1;
+  upk2(q, q0, q1);
+  upk2(r, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 
 // Item j of this CTA -> (image, head, query tile).  Consecutive items share (b, h); the tile order flips on every
@@ -116,7 +140,13 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int nvalid, ui
   for (int j = 0; j < W; j += 2) {
     float t0, t1;
     upk2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-    float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+    float p0, p1;
+    if (((j >> 1) & 3) >= 4 - kPolyPairs) {
+      ex2_poly_pair(t0, t1, p0, p1);
+    } else {
+      p0 = ex2_approx(t0);
+      p1 = ex2_approx(t1);
+    }
     if (MASKED) {
       if (j >= nvalid) p0 = 0.f;
       if (j + 1 >= nvalid) p1 = 0.f;
@@ -244,9 +274,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int n16 = p.SK / 16;                    // 16-column score chunks; only the last one can hold masked keys
     const int last_valid = p.S - (n16 - 1) * 16;  // valid columns in it (1..16)
     const uint64_t scale2 = pk2(p.scale_log2e, p.scale_log2e);
+    // Item bookkeeping without divisions inside the loop (item_of costs two integer divisions, and the compiler
+    // re-derived it after every barrier wait: 11 % of the softmax warps' instructions): this group's items are
+    // j = grp, grp + 2, ...; the (image, head) pair index advances by dql * gridDim.x per iteration.
+    const int dql = p.n_mt == 2 ? 1 : 2;
+    const int step_pairs = dql * static_cast<int>(gridDim.x);
+    const int db = step_pairs / p.heads, dh = step_pairs - db * p.heads;
+    Item it = item_of(p, grp);
+    int ql = grp / p.n_mt;
 #pragma unroll 1
     for (int j = grp; j < n_items; j += 2) {
-      const Item it = item_of(p, j);
       const uint32_t ph = (j >> 1) & 1;
       const int qrow0 = it.mt * kQRows + quad * 32;
       const bool warp_live = qrow0 < p.S;  // rows 224..255 of the second tile when S = 197: nothing to do
@@ -361,6 +398,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
+      // next item of this group
+      ql += dql;
+      it.h += dh;
+      it.b += db;
+      if (it.h >= p.heads) {
+        it.h -= p.heads;
+        ++it.b;
+      }
+      if (p.n_mt == 2) it.mt ^= 1;  // s = grp is fixed, the tile order flips with ql
     }
   }
 
