@@ -36,7 +36,7 @@ struct Cfg2 {
   static constexpr int kABytes = BM * kStageRowBytes;
   static constexpr int kBBytes = (BN / 2) * kStageRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = EW * kStgBytes;
+  static constexpr int kStagingBytes = EW * kStgBytes * kStgBufs;
   static constexpr int kMaxStages = (232448 - 1024 - kStagingBytes - 256) / kStageBytes;
   static constexpr int kStages = kMaxStages < (BN == 128 ? 8 : 6) ? kMaxStages : (BN == 128 ? 8 : 6);
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
@@ -158,7 +158,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ epilogue warps 0..7 (both CTAs, own 128 rows)
     const int quad = warp & 3;
     const int grp = warp >> 2;
-    uint8_t* stg = staging + warp * kStgBytes;
+    uint8_t* stg = staging + warp * kStgBytes * kStgBufs;
+    int stg_sel = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -168,7 +169,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      epilogue_tile<BN, false, OUT_F32, ACT, true, EW / 4>(p, &tmO, stg, grp, lane, m0, nt0, t_row);
+      epilogue_tile<BN, false, OUT_F32, ACT, true, EW / 4, kStgBufs>(p, &tmO, stg, grp, lane, m0, nt0, t_row, &stg_sel);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(&tempty[as], 0));
