@@ -141,6 +141,74 @@ __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long
   }
 }
 
+// Narrow rows (D = 4 * LPR * NV with LPR = 8 or 16 lanes per row: 64, 96, 128, 192, ...): 32 / LPR rows per warp so that
+// every lane carries exactly NV float4 -- with a whole warp per row a D = 192 row keeps half the lanes at half load and
+// a D = 96 row (Swin stage 1) leaves a quarter of them idle (4.5 and 3.4 TB/s instead of ~6).  Statistics are reduced
+// with xor-shuffles inside the LPR-lane group.
+template <int LPR, int NV, int OUT>
+__global__ void __launch_bounds__(256) ln_rows4_sub_kernel(const float* x, long long x_stride, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, void* __restrict__ y,
+                                                           long long y_stride, float* y_copy, long long rows, float eps) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  constexpr int D = 4 * LPR * NV;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long row = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool live = row < rows;  // dead sub-rows still take part in the shuffles
+  const float* xr = x + (live ? row : 0) * x_stride;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * LPR + l) * 4;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                 : "l"(xr + c));
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(D) + eps);
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * LPR + l) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+    float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if (OUT == EVT_TF32) {
+      o0 = ptx::round_tf32(o0);
+      o1 = ptx::round_tf32(o1);
+      o2 = ptx::round_tf32(o2);
+      o3 = ptx::round_tf32(o3);
+    }
+    if (OUT == EVT_BF16) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&h0);
+      w.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * y_stride + c) = w;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * y_stride + c) = make_float4(o0, o1, o2, o3);
+    }
+    if (y_copy != nullptr) *reinterpret_cast<float4*>(y_copy + row * x_stride + c) = make_float4(o0, o1, o2, o3);
+  }
+}
+
 // Any D (odd, > 1024): warp per row, three strided passes over the row (L1/L2 resident).
 template <int OUT>
 __global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, long long x_stride,
@@ -222,7 +290,21 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
                      (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(g) % 16 == 0) && (reinterpret_cast<uintptr_t>(b) % 16 == 0) &&
                      (yc == nullptr || reinterpret_cast<uintptr_t>(yc) % 16 == 0);
-  if (fast4) {
+  // narrow rows: several rows per warp (D = 64, 96, 192 -- T2T performer, Swin stage 1, DeiT-Tiny / Swin stage 2)
+  int lpr = 0, nvs = 0;
+  if (fast4 && D == 64) lpr = 16, nvs = 1;
+  else if (fast4 && D == 96) lpr = 8, nvs = 3;
+  else if (fast4 && D == 192) lpr = 16, nvs = 3;
+  if (lpr != 0) {
+    const int rpw = 32 / lpr;
+    const unsigned gsub = static_cast<unsigned>((rows + wpb * rpw - 1) / (wpb * rpw));
+    if (D == 64)
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 1, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+    else if (D == 96)
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<8, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+    else
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+  } else if (fast4) {
     const int nv = (D + 127) / 128;
 #define EVT_LN4_CASE(NVV)                                                                          \
   case NVV:                                                                                        \

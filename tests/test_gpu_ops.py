@@ -23,7 +23,7 @@ def _rand(shape, seed, scale=1.0, device="cuda"):
 
 
 @pytest.mark.parametrize("rows,D,eps", [(197, 192, 1e-12), (197 * 3 + 5, 384, 1e-12), (1000, 768, 1e-5),
-                                        (64, 64, 1e-5), (33, 576, 1e-5), (50, 147, 1e-5), (7, 1000, 1e-12)])
+                                        (64, 64, 1e-5), (33, 576, 1e-5), (50, 147, 1e-5), (7, 1000, 1e-12), (101, 96, 1e-5), (3, 64, 1e-5)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
 def test_layernorm(rows, D, eps, out_dtype):
     ops = _ops()
