@@ -47,7 +47,8 @@ struct AttnParams {
   const float* head_mask;
   long long ldc;
   int S, SK, heads, B;
-  int n_mt;      // query tiles per (image, head)
+  int n_mt;      // query tiles per work unit: tiles per (image, head), or 1 when the tiles are split across CTAs
+  int q_tiles;   // query tiles per (image, head)
   int n_stages;  // shared-memory ring depth
   float scale_log2e;
 };
@@ -101,16 +102,25 @@ __device__ __forceinline__ void ex2_poly_pair(float t0, float t1, float& p0, flo
 
 // Item j of this CTA -> (image, head, query tile).  Consecutive items share (b, h); the tile order flips on every
 // other pair so that each softmax group (slot = j & 1) sees full and ragged query tiles alternately.
+// Small batches (fewer work units than SMs) split the query tiles of a pair across CTAs instead (n_mt = 1, unit =
+// (pair, tile)): batch 1 with 12 heads then runs on 24 SMs, one tile each, instead of 12 SMs with two tiles in sequence.
 struct Item {
   int b, h, mt;
 };
 __device__ __forceinline__ Item item_of(const AttnParams& p, int j) {
   const int ql = j / p.n_mt;
   const int s = j - ql * p.n_mt;
-  const int pair = blockIdx.x + ql * gridDim.x;
+  const int unit = blockIdx.x + ql * gridDim.x;
   Item it;
-  it.b = pair / p.heads;
-  it.h = pair - it.b * p.heads;
+  if (p.n_mt != p.q_tiles) {  // split mode: unit = pair * q_tiles + tile
+    const int pair = unit / p.q_tiles;
+    it.mt = unit - pair * p.q_tiles;
+    it.b = pair / p.heads;
+    it.h = pair - it.b * p.heads;
+    return it;
+  }
+  it.b = unit / p.heads;
+  it.h = unit - it.b * p.heads;
   it.mt = p.n_mt == 2 ? (s ^ (ql & 1)) : s;
   return it;
 }
@@ -175,9 +185,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int a = p.heads * kHD;
-  const int total_pairs = p.B * p.heads;
-  const int my_pairs = (total_pairs - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int n_items = my_pairs * p.n_mt;
+  const int total_units = p.B * p.heads * (p.q_tiles / p.n_mt);
+  const int my_units = (total_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_items = my_units * p.n_mt;
 
   if (warp == kProdWarp && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
@@ -281,7 +291,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int step_pairs = dql * static_cast<int>(gridDim.x);
     const int db = step_pairs / p.heads, dh = step_pairs - db * p.heads;
     Item it = item_of(p, grp);
-    int ql = grp / p.n_mt;
 #pragma unroll 1
     for (int j = grp; j < n_items; j += 2) {
       const uint32_t ph = (j >> 1) & 1;
@@ -399,14 +408,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       // next item of this group
-      ql += dql;
+      if (p.n_mt != p.q_tiles) {  // split mode (small batches only): units are (pair, tile), no incremental form
+        if (j + 2 < n_items) it = item_of(p, j + 2);
+        continue;
+      }
       it.h += dh;
       it.b += db;
       if (it.h >= p.heads) {
         it.h -= p.heads;
         ++it.b;
       }
-      if (p.n_mt == 2) it.mt ^= 1;  // s = grp is fixed, the tile order flips with ql
+      if (p.n_mt == 2) it.mt ^= 1;  // s = grp is fixed, the tile order flips with every step of ql
     }
   }
 
@@ -627,7 +639,9 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   p.SK = SK;
   p.heads = heads;
   p.B = B;
-  p.n_mt = (S + kQRows - 1) / kQRows;
+  p.q_tiles = (S + kQRows - 1) / kQRows;
+  const long long n_pairs = static_cast<long long>(B) * heads;
+  p.n_mt = (p.q_tiles > 1 && n_pairs * p.q_tiles <= num_sms()) ? 1 : p.q_tiles;  // split the tiles across CTAs at small batch
   p.scale_log2e = scale * 1.4426950408889634f;
   const int stage_bytes = kQRows * 128 + 2 * SK * 128;
   const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
@@ -644,8 +658,8 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
     EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured_dev = dev;
   }
-  const long long pairs = static_cast<long long>(B) * heads;
-  const int grid = pairs < num_sms() ? static_cast<int>(pairs) : num_sms();
+  const long long units = n_pairs * (p.q_tiles / p.n_mt);
+  const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
   EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_rows(static_cast<long long>(B) * S), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;
