@@ -15,6 +15,11 @@ int fail(int code, const std::string& msg) {
 }
 void count_launch(int n) { g_launches += n; }
 
+static thread_local int g_static_weights = 0;
+bool gemm_weights_static() { return g_static_weights > 0; }
+StaticWeightsScope::StaticWeightsScope() { ++g_static_weights; }
+StaticWeightsScope::~StaticWeightsScope() { --g_static_weights; }
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

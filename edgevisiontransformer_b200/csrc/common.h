@@ -61,6 +61,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = allow ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// Model runtime scope: the W operands of the GEMMs launched inside are weights owned by the library (never written by a
+// preceding kernel), which lets the small-M kernel prefetch them ahead of the programmatic dependency wait.
+bool gemm_weights_static();
+struct StaticWeightsScope {
+  StaticWeightsScope();
+  ~StaticWeightsScope();
+};
 bool gemm_ln_fusion_enabled();  // EVT_FUSE_LN=1 routes the model runtime through the experimental GEMM+LayerNorm kernel
 bool gemm_split_k_enabled();  // evt_gemm_set_split_k / EVT_GEMM_SPLIT_K
 int gemm_pair_mode();  // -1 auto, 0 never, 1 whenever applicable (evt_gemm_set_pair_mode / EVT_GEMM_PAIR)

@@ -63,6 +63,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   ptx::grid_dep_launch();  // the next kernel may begin its own prologue
+  // Latency path: when the caller vouches that W is not produced by the preceding kernel (model weights), the W tiles of
+  // the first pipeline stages are requested BEFORE the dependency wait, so their HBM round trip (weights are cold at batch
+  // 1: each is read once per forward) overlaps the previous kernel's tail under programmatic dependent launch.
+  int w_pre = 0;
+  if (p.w_static && warp == kProducerWarp && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) {
+    const int item = blockIdx.x;
+    const int tile = item / p.k_splits;
+    const int kb0 = (item - tile * p.k_splits) * p.kb_per_split;
+    const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+    const int n0 = (tile % p.tiles_n) * BN;
+    w_pre = min(C::kStages, kb1 - kb0);
+    for (int i = 0; i < w_pre; ++i) {
+      ptx::mbar_arrive_expect_tx(&full[i], C::kStageBytes);
+      ptx::tma_load_2d_hint(stage_base + i * C::kStageBytes + C::kABytes, &tmW, &full[i], (kb0 + i) * p.k_step, n0, ptx::kEvictLast);
+    }
+  }
   ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
@@ -77,9 +93,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = (tile / p.tiles_n) * BM;
         const int n0 = (tile % p.tiles_n) * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
+          if (w_pre > 0) {  // first stages of the first item: barrier armed and W already in flight
+            --w_pre;
+            ptx::tma_load_2d(sa, &tmA, &full[stage], kb * p.k_step, m0);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
           ptx::tma_load_2d(sa, &tmA, &full[stage], kb * p.k_step, m0);
           ptx::tma_load_2d_hint(sb, &tmW, &full[stage], kb * p.k_step, n0, ptx::kEvictLast);
@@ -276,6 +301,7 @@ int gemm_launch(const void* A, int64_t lda, const void* W, int64_t ldw, int in_d
   p.tiles_n = (N + bn - 1) / bn;
   p.num_kb = (K + k_step - 1) / k_step;
   p.k_step = k_step;
+  p.w_static = gemm_weights_static() ? 1 : 0;
   {
     const int oe = out_dtype != EVT_BF16 ? 4 : 2;
     bool ok = reinterpret_cast<uintptr_t>(out) % 16 == 0 && (ldo * oe) % 16 == 0;

@@ -51,6 +51,8 @@ struct GemmParams {
   int k_step;  // elements of K per stage (64 bf16 / 32 tf32)
   int vec_ok;  // out / residual / bias allow 16-byte vector access
   int round_tf32;  // f32 output feeds a tf32 tensor-core op: round to nearest tf32 when written
+  int w_static;    // W is not written by the preceding kernel on the stream (model weights): its first tiles may be
+                   // requested before griddepcontrol.wait (1-CTA kernel, latency path)
 };
 
 __device__ __forceinline__ long long map_out_row(const GemmParams& p, long long row) {

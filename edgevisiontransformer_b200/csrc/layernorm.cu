@@ -76,14 +76,29 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
 
 // D % 4 == 0, D <= 1024, strides % 4 == 0: 16-byte loads (512 B per warp instruction), 8-byte bf16 / 16-byte f32 stores.
 // NV = ceil(D / 128).  The input is read with a streaming (no L1 allocate) hint: nothing here is touched twice.
-template <int NV, int OUT>
+// PRE (latency path, few rows): gamma / beta are fetched into registers BEFORE griddepcontrol.wait -- they do not depend on
+// the previous kernel, so under programmatic dependent launch that round trip overlaps the previous kernel's tail instead of
+// following the row statistics (three dependent memory round trips per LayerNorm become two; 25 LayerNorms per forward).
+// Not used at large batch: 48 more live registers would halve the occupancy of a kernel that runs at the HBM roofline.
+template <int NV, int OUT, bool PRE = false>
 __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long x_stride,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        void* __restrict__ y, long long y_stride, float* y_copy,
                                                        long long rows, int D, float eps) {
   ptx::grid_dep_launch();
-  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
+  float4 gpre[PRE ? NV : 1], bpre[PRE ? NV : 1];
+  if (PRE) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (c < D) {
+        gpre[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        bpre[i] = __ldg(reinterpret_cast<const float4*>(beta + c));
+      }
+    }
+  }
+  ptx::grid_dep_wait();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * x_stride;
@@ -115,8 +130,8 @@ __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
     if (c < D) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 g = PRE ? gpre[i] : __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = PRE ? bpre[i] : __ldg(reinterpret_cast<const float4*>(beta + c));
       float o0 = (v[i].x - mean) * rstd * g.x + b.x;
       float o1 = (v[i].y - mean) * rstd * g.y + b.y;
       float o2 = (v[i].z - mean) * rstd * g.z + b.z;
@@ -308,7 +323,10 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
     const int nv = (D + 127) / 128;
 #define EVT_LN4_CASE(NVV)                                                                          \
   case NVV:                                                                                        \
-    EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
+    if (rows <= 4096)                                                                              \
+      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT, true>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
+    else                                                                                           \
+      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     break;
     switch (nv) {
       EVT_LN4_CASE(1) EVT_LN4_CASE(2) EVT_LN4_CASE(3) EVT_LN4_CASE(4) EVT_LN4_CASE(5) EVT_LN4_CASE(6) EVT_LN4_CASE(7)

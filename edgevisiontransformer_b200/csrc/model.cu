@@ -369,6 +369,7 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   Workspace w = plan_workspace(m, batch, base);
   EVT_CHECK_ARG(w.bytes + slack <= workspace_bytes, "workspace too small for this batch (see evt_model_workspace_bytes)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StaticWeightsScope weights_are_static;  // every GEMM below multiplies by a weight matrix this model owns
   const int D = s.hidden;
   const int64_t M = static_cast<int64_t>(batch) * s.tokens;
   const int64_t Mp = static_cast<int64_t>(batch) * m->patches;
