@@ -660,7 +660,7 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   }
   const long long units = n_pairs * (p.q_tiles / p.n_mt);
   const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
-  EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_rows(static_cast<long long>(B) * S), tmQ, tmKV, p));
+  EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;
 }
@@ -702,7 +702,7 @@ int attention_tf32_launch(const float* qkv, int64_t ldq, float* ctx, int64_t ldc
     configured_dev = dev;
   }
   dim3 grid((S + kQRows - 1) / kQRows, heads, B);
-  EVT_CUDA(launch_pdl(attention_tf32_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_for_rows(static_cast<long long>(B) * S), tmQ, tmKV, p));
+  EVT_CUDA(launch_pdl(attention_tf32_kernel, grid, dim3(kAttnThreads), smem, stream, pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_tf32_kernel");
   return EVT_OK;
 }

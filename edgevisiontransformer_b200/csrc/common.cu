@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace evt {
@@ -53,6 +54,19 @@ static std::atomic<int> g_pair_mode{[] {
   const char* e = getenv("EVT_GEMM_PAIR");
   return e == nullptr ? -1 : atoi(e);
 }()};
+long long pdl_max_rows() {
+  static const long long v = [] {
+    const char* e = getenv("EVT_PDL_MAX_ROWS");
+    return e ? atoll(e) : kPdlMaxRows;
+  }();
+  return v;
+}
+
+bool pdl_rows_overridden() {
+  static const bool v = getenv("EVT_PDL_MAX_ROWS") != nullptr;
+  return v;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("EVT_PDL");

@@ -42,7 +42,23 @@ bool pdl_enabled();  // EVT_PDL=0 launches every kernel with full stream seriali
 // previous kernel's tail); at large batch, where every kernel runs for 100+ us, it measured 2 % SLOWER (CTAs parked in
 // griddepcontrol.wait), so only launches over at most this many rows (tokens) ask for it.
 constexpr long long kPdlMaxRows = 32768;
-inline bool pdl_for_rows(long long rows) { return rows <= kPdlMaxRows && pdl_enabled(); }
+long long pdl_max_rows();  // kPdlMaxRows, or EVT_PDL_MAX_ROWS from the environment (tuning: then rows alone decide)
+bool pdl_rows_overridden();
+inline bool pdl_for_rows(long long rows) { return rows <= pdl_max_rows() && pdl_enabled(); }
+// What decides is the kernel's duration, not its row count: launches shorter than ~50-100 us gain from the overlap
+// (DeiT-Small batch 256 +2.9 %, pruned DeiT-Tiny batch 1024 +1.5 %, T2T-ViT-14 +1.1 %), longer ones lose (DeiT-Base at
+// 50 k rows -1 %, at 200 k rows -1.6 %).  Proxies: elements touched for the memory-bound kernels, FLOPs for the GEMMs.
+constexpr long long kPdlMaxElems = 24ll << 20;        // rows x row length
+constexpr double kPdlMaxGemmFlops = 100e9;            // 2 M N K
+inline bool pdl_for_work(long long rows, long long row_len) {
+  if (pdl_rows_overridden()) return pdl_for_rows(rows);
+  return (rows <= kPdlMaxRows || rows * row_len <= kPdlMaxElems) && pdl_enabled();
+}
+inline bool pdl_for_gemm(long long M, long long N, long long K) {
+  if (pdl_rows_overridden()) return pdl_for_rows(M);
+  return (M <= kPdlMaxRows || 2.0 * static_cast<double>(M) * static_cast<double>(N) * static_cast<double>(K) <= kPdlMaxGemmFlops) &&
+         pdl_enabled();
+}
 
 // Launch with programmatic dependent launch allowed: the kernel must call ptx::grid_dep_wait() before its first
 // global-memory access.  (cudaLaunchKernelEx also honours a compile-time __cluster_dims__.)

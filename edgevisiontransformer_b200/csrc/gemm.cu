@@ -235,7 +235,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tm
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  EVT_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, pdl_for_rows(p.M), tmA, tmW, tmO, p));
+  EVT_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, pdl_for_gemm(p.M, p.N, p.K), tmA, tmW, tmO, p));
   EVT_LAUNCH_CHECK("gemm_kernel");
   return EVT_OK;
 }

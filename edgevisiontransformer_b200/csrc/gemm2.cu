@@ -221,7 +221,7 @@ int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtens
   p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  EVT_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, pdl_for_rows(p.M), tmA, tmW, tmO, p));
+  EVT_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, pdl_for_gemm(p.M, p.N, p.K), tmA, tmW, tmO, p));
   EVT_LAUNCH_CHECK("gemm_pair_kernel");
   return EVT_OK;
 }

@@ -314,19 +314,19 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
     const int rpw = 32 / lpr;
     const unsigned gsub = static_cast<unsigned>((rows + wpb * rpw - 1) / (wpb * rpw));
     if (D == 64)
-      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 1, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 1, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, eps));
     else if (D == 96)
-      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<8, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<8, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, eps));
     else
-      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, eps));
+      EVT_CUDA(launch_pdl(ln_rows4_sub_kernel<16, 3, OUT>, dim3(gsub), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, eps));
   } else if (fast4) {
     const int nv = (D + 127) / 128;
 #define EVT_LN4_CASE(NVV)                                                                          \
   case NVV:                                                                                        \
     if (rows <= 4096)                                                                              \
-      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT, true>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
+      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT, true>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     else                                                                                           \
-      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
+      EVT_CUDA(launch_pdl(ln_rows4_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     break;
     switch (nv) {
       EVT_LN4_CASE(1) EVT_LN4_CASE(2) EVT_LN4_CASE(3) EVT_LN4_CASE(4) EVT_LN4_CASE(5) EVT_LN4_CASE(6) EVT_LN4_CASE(7)
@@ -334,12 +334,12 @@ int launch_rows(const float* x, long long xs, const float* g, const float* b, vo
     }
 #undef EVT_LN4_CASE
   } else if (!fast) {
-    EVT_CUDA(launch_pdl(ln_rows_generic_kernel<OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps));
+    EVT_CUDA(launch_pdl(ln_rows_generic_kernel<OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, D, eps));
   } else {
     const int nv = (D + 63) / 64;
 #define EVT_LN_CASE(NVV)                                                                          \
   case NVV:                                                                                       \
-    EVT_CUDA(launch_pdl(ln_rows_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_rows(rows), x, xs, g, b, y, ys, yc, rows, D, eps)); \
+    EVT_CUDA(launch_pdl(ln_rows_kernel<NVV, OUT>, dim3(grid), dim3(wpb * 32), 0, st, pdl_for_work(rows, D), x, xs, g, b, y, ys, yc, rows, D, eps)); \
     break;
     switch (nv) {
       EVT_LN_CASE(1) EVT_LN_CASE(2) EVT_LN_CASE(3) EVT_LN_CASE(4) EVT_LN_CASE(5) EVT_LN_CASE(6) EVT_LN_CASE(7)
