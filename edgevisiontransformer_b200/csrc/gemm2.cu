@@ -93,6 +93,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   ptx::grid_dep_launch();  // the next kernel may begin its own prologue
+  // Model-owned weights do not depend on the previous kernel: request the W half-tiles of the first pipeline stages before
+  // the dependency wait (see gemm.cu; matters when programmatic dependent launch is on, i.e. for launches under ~100 us).
+  int w_pre = 0;
+  if (p.w_static && warp == kProducerWarp && lane == 0 && pair < num_tiles) {
+    const int n0 = (pair % p.tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+    w_pre = min(C::kStages, p.num_kb);
+    for (int i = 0; i < w_pre; ++i) {
+      if (rank == 0) ptx::mbar_arrive_expect_tx(&full[i], 2 * C::kStageBytes);
+      ptx::tma_load_2d_pair(stage_base + i * C::kStageBytes + C::kABytes, &tmW, ptx::mapa(&full[i], 0), i * p.k_step, n0, ptx::kEvictLast);
+    }
+  }
   ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
@@ -104,15 +115,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
           const uint32_t lead_full = ptx::mapa(&full[stage], 0);
-          // The leader expects the bytes of both CTAs; the peer's bytes may land first (the transaction count goes
-          // transiently negative, the phase cannot complete before the leader's arrive) -- no remote arrive needed.
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
-          ptx::tma_load_2d_pair(sa, &tmA, lead_full, kb * p.k_step, m0, ptx::kEvictNormal);
-          ptx::tma_load_2d_pair(sb, &tmW, lead_full, kb * p.k_step, n0, ptx::kEvictLast);
+          if (w_pre > 0) {  // first stages of the first tile: barrier armed and W already in flight
+            --w_pre;
+            ptx::tma_load_2d_pair(sa, &tmA, lead_full, kb * p.k_step, m0, ptx::kEvictNormal);
+          } else {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            // The leader expects the bytes of both CTAs; the peer's bytes may land first (the transaction count goes
+            // transiently negative, the phase cannot complete before the leader's arrive) -- no remote arrive needed.
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            ptx::tma_load_2d_pair(sa, &tmA, lead_full, kb * p.k_step, m0, ptx::kEvictNormal);
+            ptx::tma_load_2d_pair(sb, &tmW, lead_full, kb * p.k_step, n0, ptx::kEvictLast);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
