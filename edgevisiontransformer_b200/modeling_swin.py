@@ -74,6 +74,16 @@ def attention_table(bias_table: torch.Tensor, heads: int, ws: int, mask: torch.T
     return out.contiguous()
 
 
+class B200SwinConfig:
+    """The attributes the reference's callers (and eval_loop.PipelinedClassifier) read off ``model.config``."""
+
+    def __init__(self, depths, num_heads, embed_dim, window_size, patch_size, image_size, layer_norm_eps, num_labels):
+        self.depths, self.num_heads, self.embed_dim = list(depths), list(num_heads), embed_dim
+        self.window_size, self.patch_size, self.image_size = window_size, patch_size, image_size
+        self.layer_norm_eps, self.num_labels = layer_norm_eps, num_labels
+        self.hidden_size = embed_dim * 2 ** (len(self.depths) - 1)
+
+
 class B200SwinForImageClassification(nn.Module):
     """Inference-only.  ``state_dict`` uses HF key names (``swin.embeddings...``, ``swin.encoder.layers.{s}.blocks.{b}...``)."""
 
@@ -145,6 +155,7 @@ class B200SwinForImageClassification(nn.Module):
         self.g_final, self.b_final = f32("swin.layernorm.weight"), f32("swin.layernorm.bias")
         self.w_cls, self.b_cls = bf16("classifier.weight"), f32("classifier.bias")
         self.num_labels = self.w_cls.shape[0]
+        self.config = B200SwinConfig(depths, num_heads, embed_dim, window, patch, image_size, eps, self.num_labels)
         self._param = nn.Parameter(self.b_cls, requires_grad=False)       # next(model.parameters()).device works
 
     # ------------------------------------------------------------------ constructors

@@ -84,3 +84,20 @@ def test_swin_matches_oracle_and_golden(golden_dir, name, depths, seed, bs):
         m(x)                                                           # CPU input: no fallback
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 192, 192, device="cuda"))
+
+
+def test_swin_through_the_eval_loop():
+    """The eval loop of the path's caller (deit_pruning/src/utils.py:151-228) drives the Swin model as well."""
+    from edgevisiontransformer_b200.eval_loop import PipelinedClassifier, evaluate
+    from edgevisiontransformer_b200.modeling_swin import B200SwinForImageClassification
+    hf = osw.build_hf_swin("tiny", seed=8, stress=True, depths=[1, 1, 3, 1])
+    m = B200SwinForImageClassification.from_hf(hf, max_batch=4)
+    x = ovit.synthetic_images(6, seed=3)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    got = PipelinedClassifier(m, chunk=4).logits(x.pin_memory())
+    r = ovit.compare_logits(got, want)
+    assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
+    labels = want.argmax(-1)
+    res = evaluate([(x[:4], labels[:4]), (x[4:], labels[4:])], m, eval_batch_size=4)
+    assert res["eval_accuracy"] == 1.0
