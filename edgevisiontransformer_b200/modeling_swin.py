@@ -101,6 +101,7 @@ class B200SwinForImageClassification(nn.Module):
         self.depths, self.num_heads, self.embed_dim = list(depths), list(num_heads), embed_dim
         self.window, self.patch, self.image_size, self.eps = window, patch, image_size, eps
         self.max_batch, self._device = int(max_batch), dev
+        self._graphs: dict = {}
         sd = {k: v.detach() for k, v in state_dict.items()}
 
         def f32(k):
@@ -231,6 +232,20 @@ class B200SwinForImageClassification(nn.Module):
             for s in range(0, x.shape[0], self.max_batch):
                 outs.append(self._run(x[s:s + self.max_batch]))
         return ImageClassifierOutput(logits=outs[0] if len(outs) == 1 else torch.cat(outs, 0))
+
+
+def _swin_forward_graphed(self, pixel_values: torch.Tensor) -> ImageClassifierOutput:
+    """Same result as forward(); the ~110 launches of one forward are replayed from a CUDA graph (latency path)."""
+    if not pixel_values.is_cuda:
+        raise RuntimeError("pixel_values must be a CUDA tensor (no CPU fallback)")
+    if pixel_values.shape[0] > self.max_batch:
+        return self.forward(pixel_values)
+    from .graph_util import graphed_call
+    with torch.no_grad():
+        return ImageClassifierOutput(logits=graphed_call(self._graphs, pixel_values, self._run, self._device))
+
+
+B200SwinForImageClassification.forward_graphed = _swin_forward_graphed
 
 
 def microsoft_to_hf(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -94,6 +94,7 @@ class B200T2TViT(nn.Module):
             c, device=dev, max_batch=max_batch, dialect="tf", hidden_act="gelu_tanh", layer_norm_eps=TF_EPS, final_ln=True,
             head_size=D // num_heads, embed_k=sd["t2t.project.kernel"].shape[0], precision=precision)
         self.config = self.core.config
+        self._graphs: dict = {}
         self.eval()
 
     @torch.no_grad()
@@ -116,6 +117,17 @@ class B200T2TViT(nn.Module):
                 pm = self.tokens(x[s:s + self.max_batch])
                 outs.append(self.core.forward_embedded(pm).logits)
         return ImageClassifierOutput(logits=torch.cat(outs) if len(outs) > 1 else outs[0])
+
+    @torch.no_grad()
+    def forward_graphed(self, x: torch.Tensor) -> ImageClassifierOutput:
+        """Same result as forward(); front-end and encoder launches replayed from one CUDA graph (latency path)."""
+        if not x.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
+        if x.shape[0] > self.max_batch:
+            return self.forward(x)
+        from .graph_util import graphed_call
+        return ImageClassifierOutput(logits=graphed_call(
+            self._graphs, x, lambda xin: self.core.forward_embedded(self.tokens(xin)).logits, self._dev))
 
     def launches_per_forward(self) -> int:
         return 2 * 9 + 1 + self.core.launches_per_forward() - 1

@@ -172,6 +172,9 @@ def test_t2t_front_end_and_model():
     assert r["max_abs"] <= 3e-2 and r["top1_agree"] == 1.0, r
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 224, 224, device="cuda"))
+    for _ in range(2):                                   # latency path: one CUDA graph over front-end + encoder
+        r = ovit.compare_logits(m.forward_graphed(x.cuda()).logits, want_logits)
+        assert r["max_abs"] <= 3e-2 and r["top1_agree"] == 1.0, r
 
 
 def test_stage_profile_tap():

@@ -101,3 +101,7 @@ def test_swin_through_the_eval_loop():
     labels = want.argmax(-1)
     res = evaluate([(x[:4], labels[:4]), (x[4:], labels[4:])], m, eval_batch_size=4)
     assert res["eval_accuracy"] == 1.0
+    # latency path: CUDA-graph replay gives the same logits as the eager launch sequence
+    for _ in range(2):
+        r = ovit.compare_logits(m.forward_graphed(x[:2].cuda()).logits, want[:2])
+        assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
