@@ -13,6 +13,8 @@
 // once) while the whole weight matrix stays in L2.  M, N and K tails are handled by TMA zero fill on the
 // load side and by clipping / predication on the store side, so no operand is ever padded in HBM (only leading
 // dimensions must be multiples of 16 bytes).
+#include <cstdlib>
+
 #include "gemm_common.cuh"
 #include "ops.h"
 
@@ -194,6 +196,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // Tile width: the one that pads N least; when that leaves SMs without a tile (small M: the latency path), the
 // narrower width that puts the most CTAs to work.
 int choose_bn(int64_t M, int N) {
+  // tuning override: EVT_GEMM_BN="N:bn[,N:bn...]" forces the tile width for the given output widths
+  static const char* force = getenv("EVT_GEMM_BN");
+  if (force != nullptr) {
+    for (const char* q = force; *q != 0;) {
+      const long n = strtol(q, const_cast<char**>(&q), 10);
+      if (*q != ':') break;
+      const long bn = strtol(q + 1, const_cast<char**>(&q), 10);
+      if (n == N && (bn == 256 || bn == 192 || bn == 128 || bn == 64)) return static_cast<int>(bn);
+      if (*q == ',') ++q;
+    }
+  }
   const int cands[4] = {256, 192, 128, 64};
   const long tiles_m = static_cast<long>((M + BM - 1) / BM);
   int best = 256;
