@@ -47,6 +47,7 @@ SIGNATURES = {
     "evt_launch_count_reset": (None, []),
     "evt_gemm_set_pair_mode": (None, [_i]),
     "evt_gemm_set_split_k": (None, [_i]),
+    "evt_gemm_weights_static": (None, [_i]),
     "evt_layernorm_fwd": (_i, [_p, _i64, _p, _p, _p, _i, _i64, _p, _i64, _i, _f, _p]),
     "evt_layernorm2d_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p]),
     "evt_gemm_bias_act": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _p, _i, _i64, _i, _i, _i, _i64, _i, _i, _i, _p]),

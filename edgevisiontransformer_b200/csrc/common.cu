@@ -20,6 +20,10 @@ static thread_local int g_static_weights = 0;
 bool gemm_weights_static() { return g_static_weights > 0; }
 StaticWeightsScope::StaticWeightsScope() { ++g_static_weights; }
 StaticWeightsScope::~StaticWeightsScope() { --g_static_weights; }
+void gemm_weights_static_add(int delta) {
+  g_static_weights += delta;
+  if (g_static_weights < 0) g_static_weights = 0;
+}
 
 int num_sms() {
   static int cached[64] = {0};
@@ -135,3 +139,5 @@ int evt_device_check(void) {
 }
 
 }  // extern "C"
+
+extern "C" void evt_gemm_weights_static(int delta) { evt::gemm_weights_static_add(delta); }

@@ -80,6 +80,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // Model runtime scope: the W operands of the GEMMs launched inside are weights owned by the library (never written by a
 // preceding kernel), which lets the small-M kernel prefetch them ahead of the programmatic dependency wait.
 bool gemm_weights_static();
+void gemm_weights_static_add(int delta);  // evt_gemm_weights_static
 struct StaticWeightsScope {
   StaticWeightsScope();
   ~StaticWeightsScope();

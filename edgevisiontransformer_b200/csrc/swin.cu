@@ -107,11 +107,91 @@ __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict_
   }
 }
 
+// G = 1 with narrow rows (C = 96 / 192: Swin stages 1 and 2): 32 / LPR rows per warp, every lane carries NV float4
+// (a whole warp per 96-float row leaves a quarter of the lanes idle; these launches cover 802 816 rows at batch 256).
+template <int LPR, int NV, bool OUT_BF16>
+__global__ void __launch_bounds__(256) gather_ln_sub_kernel(const float* __restrict__ x, const int* __restrict__ idx,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            void* __restrict__ y, float* __restrict__ copy, long long rows_out,
+                                                            int T_in, int T_out, float eps) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  constexpr int C = 4 * LPR * NV;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long row = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool live = row < rows_out;
+  const long long r = live ? row : 0;
+  const long long img = r / T_out;
+  const int src = __ldg(idx + static_cast<int>(r - img * T_out));
+  const float* xr = x + (img * T_in + src) * static_cast<long long>(C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * LPR + l) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  if (live && copy != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(copy + row * C + (i * LPR + l) * 4) = v[i];
+  }
+  if (y == nullptr) return;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * LPR + l) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if (OUT_BF16) {
+      uint2 o;
+      o.x = pack_bf16(o0, o1);
+      o.y = pack_bf16(o2, o3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C + c) = o;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * C + c) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
+template <int LPR, int NV>
+int launch_gather_ln_sub(const float* x, const int* idx, const float* gamma, const float* beta, void* y, int y_dtype, float* copy,
+                         long long rows_out, int T_in, int T_out, float eps, cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const unsigned grid = static_cast<unsigned>((rows_out + 8 * RPW - 1) / (8 * RPW));
+  const bool pdl = pdl_for_work(rows_out, 4 * LPR * NV);
+  if (y_dtype == EVT_BF16)
+    EVT_CUDA(launch_pdl(gather_ln_sub_kernel<LPR, NV, true>, dim3(grid), dim3(256), 0, st, pdl, x, idx, gamma, beta, y, copy, rows_out,
+                        T_in, T_out, eps));
+  else
+    EVT_CUDA(launch_pdl(gather_ln_sub_kernel<LPR, NV, false>, dim3(grid), dim3(256), 0, st, pdl, x, idx, gamma, beta, y, copy, rows_out,
+                        T_in, T_out, eps));
+  EVT_LAUNCH_CHECK("gather_ln_sub_kernel");
+  return EVT_OK;
+}
+
 template <int NV>
 int launch_gather_ln(const float* x, const int* idx, const float* gamma, const float* beta, void* y, int y_dtype, float* copy,
                      long long rows_out, int T_in, int T_out, int G, int C, float eps, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((rows_out + 7) / 8);
-  const bool pdl = pdl_for_rows(rows_out);
+  const bool pdl = pdl_for_work(rows_out, static_cast<long long>(G) * C);
   if (y_dtype == EVT_BF16)
     EVT_CUDA(launch_pdl(gather_ln_kernel<NV, true>, dim3(grid), dim3(256), 0, st, pdl, x, idx, gamma, beta, y, copy, rows_out, T_in,
                         T_out, G, C, eps));
@@ -385,6 +465,8 @@ extern "C" int evt_gather_layernorm(const float* x, const int* idx, const float*
   const long long rows = images * T_out;
   const int D = G * C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G == 1 && C == 96) return launch_gather_ln_sub<8, 3>(x, idx, gamma, beta, y, y_dtype, copy_f32, rows, T_in, T_out, eps, st);
+  if (G == 1 && C == 192) return launch_gather_ln_sub<16, 3>(x, idx, gamma, beta, y, y_dtype, copy_f32, rows, T_in, T_out, eps, st);
   const int nv = (D + 127) / 128;
   if (nv <= 1) return launch_gather_ln<1>(x, idx, gamma, beta, y, y_dtype, copy_f32, rows, T_in, T_out, G, C, eps, st);
   if (nv <= 2) return launch_gather_ln<2>(x, idx, gamma, beta, y, y_dtype, copy_f32, rows, T_in, T_out, G, C, eps, st);
@@ -419,7 +501,7 @@ extern "C" int evt_window_attention_fwd(const void* qkv, int64_t ldq, void* ctx,
   const long long cap = static_cast<long long>(num_sms()) * 4;  // 4 CTAs of 48 KB per SM, grid-stride over the rest
   const unsigned grid = static_cast<unsigned>(ctas_needed < cap ? ctas_needed : cap);
   EVT_CUDA(launch_pdl(window_attention_kernel, dim3(grid), dim3(kWWarps * 32), smem, static_cast<cudaStream_t>(stream),
-                      pdl_for_rows(n_windows * kWTok), reinterpret_cast<const __nv_bfloat16*>(qkv), static_cast<long long>(ldq),
+                      pdl_for_work(n_windows * kWTok, static_cast<long long>(heads) * kWHd), reinterpret_cast<const __nv_bfloat16*>(qkv), static_cast<long long>(ldq),
                       reinterpret_cast<__nv_bfloat16*>(ctx), static_cast<long long>(ldc), table, n_tab, heads, items,
                       scale * 1.4426950408889634f));
   EVT_LAUNCH_CHECK("window_attention_kernel");

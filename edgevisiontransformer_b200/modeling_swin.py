@@ -190,6 +190,10 @@ class B200SwinForImageClassification(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _run(self, x: torch.Tensor) -> torch.Tensor:
+        with ops.static_weights():          # every linear() below multiplies by a weight matrix this module owns
+            return self._run_impl(x)
+
+    def _run_impl(self, x: torch.Tensor) -> torch.Tensor:
         B = x.shape[0]
         eps, ws2 = self.eps, self.window * self.window
         cols = ops.im2col_patch(x, self.patch)

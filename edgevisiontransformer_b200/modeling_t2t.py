@@ -100,8 +100,9 @@ class B200T2TViT(nn.Module):
     @torch.no_grad()
     def tokens(self, x: torch.Tensor) -> torch.Tensor:
         """tokens-to-token module up to (not including) ``project``: bf16 [B*196, 576]."""
-        y = self.p1(x, 7, 4, 2)          # [B,56,56,64] f32
-        y = self.p2(y, 3, 2, 1)          # [B,28,28,64] f32
+        with ops.static_weights():       # the performers' linear() calls multiply by weights this module owns
+            y = self.p1(x, 7, 4, 2)          # [B,56,56,64] f32
+            y = self.p2(y, 3, 2, 1)          # [B,28,28,64] f32
         return ops.unfold_ln_nhwc(y, 3, 2, 1)
 
     @torch.no_grad()

@@ -293,6 +293,19 @@ def set_gemm_split_k(enable: bool) -> None:
     _lib.load().evt_gemm_set_split_k(1 if enable else 0)
 
 
+class static_weights:
+    """Context manager: the ``w`` operands of the ``linear`` calls inside are weights (never produced by the preceding
+    kernel), so the GEMM may request their first tiles ahead of the programmatic dependency wait (evt_gemm_weights_static)."""
+
+    def __enter__(self):
+        _lib.load().evt_gemm_weights_static(1)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().evt_gemm_weights_static(-1)
+        return False
+
+
 def launch_count(reset: bool = False) -> int:
     lib = _lib.load()
     n = int(lib.evt_launch_count())

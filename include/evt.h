@@ -66,6 +66,12 @@ void evt_gemm_set_pair_mode(int mode);
  * downstream turn into logit differences of a few 1e-3, inside the 2e-2 parity budget); 0 turns it off (bit-reproducible,
  * batch-invariant results).  Large batches and the tf32 accuracy mode never split.  Initial value: environment variable EVT_GEMM_SPLIT_K if set, else 1. */
 void evt_gemm_set_split_k(int enable);
+/* Promise, for the evt_gemm_bias_act* calls the calling thread makes while the count is positive, that W is a weight matrix:
+ * not written by the launch that precedes the GEMM on its stream.  The GEMM then requests its first W tiles before the
+ * programmatic dependency wait, overlapping their HBM round trip with the previous kernel's tail (batch-1 latency path:
+ * weights are cold, each is read once per forward).  delta = +1 to enter such a region, -1 to leave it (nestable).  The
+ * model-level entry points do this themselves; it is for forwards composed from the op-level calls (Swin, T2T front-end). */
+void evt_gemm_weights_static(int delta);
 
 /* ------------------------------------------------------------------ op level ------------- */
 

@@ -17,7 +17,7 @@ LOG2E = 1.4426950408889634
 def test_gather_layernorm_matches_torch():
     from edgevisiontransformer_b200 import ops
     g = torch.Generator().manual_seed(0)
-    for (B, T_in, T_out, G, C) in [(3, 196, 196, 1, 96), (2, 784, 196, 4, 192), (2, 196, 49, 4, 768), (1, 49, 49, 1, 384)]:
+    for (B, T_in, T_out, G, C) in [(3, 196, 196, 1, 96), (2, 784, 196, 4, 192), (2, 196, 49, 4, 768), (1, 49, 49, 1, 384), (1, 49, 49, 1, 96), (3, 196, 50, 1, 192)]:
         x = torch.randn(B * T_in, C, generator=g) * 2 + 0.5
         idx = torch.stack([torch.randperm(T_in, generator=g)[:T_out] for _ in range(G)], 1).to(torch.int32).contiguous()
         gamma, beta = torch.randn(G * C, generator=g), torch.randn(G * C, generator=g)
