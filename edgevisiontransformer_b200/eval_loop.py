@@ -42,11 +42,10 @@ class PipelinedClassifier:
         # Chunk schedule: the first H2D copy cannot overlap anything, so the chunks ramp up geometrically (chunk/8, /4, /2,
         # then full chunks): every later copy hides behind the forward of the chunk before it (a forward costs ~3x its
         # copy per image), and only the first small copy is exposed.
-        bounds, s0, size = [], 0, max(1, min(self.chunk, max(64, self.chunk // 8)))
-        while s0 < B:
-            e0 = min(B, s0 + size)
-            bounds.append((s0, e0))
-            s0, size = e0, min(self.chunk, size * 2)
+        bounds, s0 = [], 0
+        for n in chunk_schedule(B, self.chunk):
+            bounds.append((s0, s0 + n))
+            s0 += n
         host_out = None
         if want_logits and host_pixels.is_pinned():
             # pinned result buffer, allocated once per batch size (cudaHostAlloc costs milliseconds); the caller owns the
@@ -88,6 +87,27 @@ class PipelinedClassifier:
     def predict(self, host_pixels: torch.Tensor) -> torch.Tensor:
         """argmax class ids [B] on the HOST; only 8 bytes per image cross PCIe on the way back."""
         return self._run(host_pixels, False).cpu()
+
+
+def chunk_schedule(batch: int, chunk: int) -> list:
+    """Chunk sizes for one host batch: a geometric ramp (chunk/8, /4, /2) up to full chunks, so that only the first, small
+    H2D copy is exposed; a short tail (less than half a chunk) is folded into the earliest ramp chunk that can take it
+    without outgrowing 3x its predecessor (its copy must still hide behind the previous forward) -- a 128-image forward at
+    the end of a 4096-image batch runs well below the large-batch rate."""
+    sizes, rem, size = [], batch, max(1, min(chunk, max(64, chunk // 8)))
+    while rem > 0:
+        n = min(size, rem)
+        sizes.append(n)
+        rem -= n
+        size = min(chunk, size * 2)
+    if len(sizes) > 2 and sizes[-1] < chunk // 2:
+        tail = sizes[-1]
+        for i in range(1, len(sizes) - 1):
+            if sizes[i] + tail <= min(chunk, 3 * sizes[i - 1]):
+                sizes[i] += tail
+                sizes.pop()
+                break
+    return sizes
 
 
 def evaluate(eval_data: Iterable, model, eval_batch_size: int = 100, device=None, result: Optional[Dict] = None,

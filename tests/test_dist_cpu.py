@@ -55,3 +55,16 @@ def test_shard_range_edges():
     assert shard_range(2, 3, 4) == (2, 2)                              # more ranks than items: empty shard
     cover = [shard_range(4096, r, 8) for r in range(8)]
     assert cover[0] == (0, 512) and cover[-1] == (3584, 4096)
+
+
+def test_chunk_schedule_properties():
+    """Host logic of the pipelined eval loop: the chunk sizes cover the batch, never exceed the chunk, ramp up by at most 3x
+    (every copy hides behind the previous forward) and do not end in a short tail when it can be folded into the ramp."""
+    from edgevisiontransformer_b200.eval_loop import chunk_schedule
+    for batch in (1, 6, 63, 64, 100, 511, 512, 1000, 1024, 2048, 4095, 4096, 5000):
+        for chunk in (4, 64, 256, 512, 1024):
+            s = chunk_schedule(batch, chunk)
+            assert sum(s) == batch and all(0 < n <= chunk for n in s), (batch, chunk, s)
+            assert all(s[i] <= 3 * s[i - 1] for i in range(1, len(s))), (batch, chunk, s)
+    assert chunk_schedule(4096, 1024) == [128, 384, 512, 1024, 1024, 1024]
+    assert chunk_schedule(512, 512) == [64, 192, 256]
