@@ -12,6 +12,7 @@ The forward runs entirely inside libevt (hand-written sm_100a kernels); torch on
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -106,7 +107,14 @@ class B200ViTForImageClassification(nn.Module):
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
         self._ws_batch = 0
+        # Chunks of one call may run on two streams (two workspaces): the persistent GEMMs of the two chunks still take turns on
+        # the SMs, but one chunk's LayerNorm (no shared memory, few registers) can sit beside the other chunk's GEMM CTA, and a
+        # kernel's tail overlaps the next chunk's kernel instead of idling SMs.  Off unless concurrent_chunks = 2.
+        self.concurrent_chunks = int(os.environ.get("EVT_CONCURRENT_CHUNKS", "1"))
+        self._ws2: Optional[torch.Tensor] = None
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[int, tuple] = {}
+        self._profiling = False
         spec = _lib.ModelSpec()
         spec.dialect = _lib.DIALECT_TF if config.dialect == "tf" else _lib.DIALECT_HF
         spec.hidden, spec.layers, spec.tokens = config.hidden_size, config.num_hidden_layers, config.tokens
@@ -239,11 +247,31 @@ class B200ViTForImageClassification(nn.Module):
             self._graphs.clear()
         return self._ws
 
-    def _run(self, pixels: torch.Tensor, logits: torch.Tensor) -> None:
+    def _run(self, pixels: torch.Tensor, logits: torch.Tensor, ws: Optional[torch.Tensor] = None) -> None:
         B = pixels.shape[0]
-        ws = self._workspace(B)
+        if ws is None:
+            ws = self._workspace(B)
         _lib.check(self._lib.evt_model_forward(self._handle, pixels.data_ptr(), B, logits.data_ptr(), ws.data_ptr(),
                                                ws.numel(), torch.cuda.current_stream().cuda_stream), "model_forward")
+
+    def _run_chunks_two_streams(self, x: torch.Tensor, logits: torch.Tensor) -> None:
+        """Even chunks on the current stream, odd chunks on a side stream with a second workspace."""
+        B = x.shape[0]
+        ws = self._workspace(self.max_batch)
+        if self._ws2 is None or self._ws2.numel() < ws.numel():
+            self._ws2 = torch.empty_like(ws)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self._device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        side.wait_stream(main)                       # inputs / output buffer are ready on the side stream too
+        for i, s in enumerate(range(0, B, self.max_batch)):
+            e = min(B, s + self.max_batch)
+            if i & 1:
+                with torch.cuda.stream(side):
+                    self._run(x[s:e], logits[s:e], self._ws2)
+            else:
+                self._run(x[s:e], logits[s:e], ws)
+        main.wait_stream(side)
 
     @torch.no_grad()
     def forward(self, pixel_values: Optional[torch.Tensor] = None, labels=None, **ignored) -> ImageClassifierOutput:
@@ -261,9 +289,12 @@ class B200ViTForImageClassification(nn.Module):
         B = x.shape[0]
         logits = torch.empty((B, c.num_labels), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self._device):
-            for s in range(0, B, self.max_batch):
-                e = min(B, s + self.max_batch)
-                self._run(x[s:e], logits[s:e])
+            if self.concurrent_chunks >= 2 and B > self.max_batch and not self._profiling:
+                self._run_chunks_two_streams(x, logits)
+            else:
+                for s in range(0, B, self.max_batch):
+                    e = min(B, s + self.max_batch)
+                    self._run(x[s:e], logits[s:e])
         return ImageClassifierOutput(logits=logits)
 
     @torch.no_grad()
@@ -328,11 +359,13 @@ class B200ViTForImageClassification(nn.Module):
     def profile_begin(self) -> None:
         """Forwards issued from now on record a CUDA event after every launch (evt_model_profile_begin)."""
         _lib.check(self._lib.evt_model_profile_begin(self._handle), "profile_begin")
+        self._profiling = True
 
     def profile_end(self) -> Dict[str, Tuple[float, int]]:
         """-> {stage: (summed device ms, launches)} over the forwards since profile_begin(); synchronises."""
         n = len(_lib.STAGES)
         ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+        self._profiling = False
         _lib.check(self._lib.evt_model_profile_end(self._handle, ms, cnt), "profile_end")
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.STAGES)}
 
