@@ -110,6 +110,91 @@ __global__ void __launch_bounds__(256) unfold_ln_kernel(const TIN* __restrict__ 
   }
 }
 
+// Compile-time window shapes, several output rows per warp: the column -> (ky, kx, c) decomposition, the LayerNorm affine
+// parameters of the lane's columns and the validity of every column are row-invariant and live in registers across the
+// rows of the warp; interior windows (93 % of a 56 x 56 output grid) skip the per-element bounds tests.  Bit-identical to
+// unfold_ln_kernel (same loads, same reduction order).
+template <typename TIN, bool LN, int KK, int CC, int ROWS>
+__global__ void __launch_bounds__(256) unfold_ln_rows_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             long long ldo, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int H, int W, int s, int p,
+                                                             int oh, int ow, long long rows) {
+  constexpr int L = KK * KK * CC, kC = KK * CC, NP = (L + 63) / 64;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
+  int koff[NP][2], kyx[NP][2];
+  float g[NP][2], be[NP][2];
+#pragma unroll
+  for (int i = 0; i < NP; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = i * 64 + 2 * lane + e;
+      const int ky = col / kC, rem = col - ky * kC, kx = rem / CC;
+      koff[i][e] = col < L ? ky * W * CC + rem : -1;
+      kyx[i][e] = (ky << 8) | kx;
+      g[i][e] = (LN && col < L) ? gamma[col] : 0.f;
+      be[i][e] = (LN && col < L) ? beta[col] : 0.f;
+    }
+  int ox = static_cast<int>(row0 % ow);
+  long long t = row0 / ow;
+  int oy = static_cast<int>(t % oh);
+  long long b = t / oh;
+#pragma unroll 1
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = row0 + r;
+    if (row >= rows) break;
+    const int iy0 = oy * s - p, ix0 = ox * s - p;
+    const bool interior = iy0 >= 0 && iy0 + KK <= H && ix0 >= 0 && ix0 + KK <= W;
+    const TIN* base = x + ((b * H + iy0) * static_cast<long long>(W) + ix0) * CC;
+    float v[NP][2];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        bool ok = koff[i][e] >= 0;
+        if (!interior) {
+          const int iy = iy0 + (kyx[i][e] >> 8), ix = ix0 + (kyx[i][e] & 255);
+          ok = ok && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        }
+        v[i][e] = ok ? static_cast<float>(base[koff[i][e]]) : 0.f;
+      }
+      sum += v[i][0] + v[i][1];
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (LN) {
+      mean = warp_sum(sum) / static_cast<float>(L);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float d0 = v[i][0] - mean, d1 = v[i][1] - mean;
+        if (koff[i][0] >= 0) q += d0 * d0;
+        if (koff[i][1] >= 0) q += d1 * d1;
+      }
+      rstd = rsqrtf(warp_sum(q) / static_cast<float>(L) + eps);
+    }
+    __nv_bfloat16* orow = out + row * ldo;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int col = i * 64 + 2 * lane;
+      if (col < ldo) {
+        float o0 = 0.f, o1 = 0.f;
+        if (koff[i][0] >= 0) o0 = LN ? (v[i][0] - mean) * rstd * g[i][0] + be[i][0] : v[i][0];
+        if (koff[i][1] >= 0) o1 = LN ? (v[i][1] - mean) * rstd * g[i][1] + be[i][1] : v[i][1];
+        *reinterpret_cast<__nv_bfloat162*>(orow + col) = __floats2bfloat162_rn(o0, o1);
+      }
+    }
+    if (++ox == ow) {
+      ox = 0;
+      if (++oy == oh) {
+        oy = 0;
+        ++b;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- performer
 // Both kernels are chains of small matrix products per 16-token tile and run them on the warp-level tensor path
 // (mma.sync m16n8k16, bf16 operands, f32 accumulate) -- the first version walked them with 128 warp shuffles per token
@@ -383,7 +468,9 @@ template <typename TIN, bool LN>
 void unfold_ln_dispatch(const TIN* xi, __nv_bfloat16* o, int64_t ldo, const float* gamma, const float* beta, float eps, int B, int H,
                         int W, int C, int k, int s, int p, int oh, int ow, long long rows, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (k == 7 && C == 3) unfold_ln_kernel<TIN, LN, 7, 3><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
+  constexpr int kRowsPerWarp = 4;
+  const unsigned grid_rows = static_cast<unsigned>((rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp));
+  if (k == 7 && C == 3) unfold_ln_rows_kernel<TIN, LN, 7, 3, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
   else if (k == 3 && C == 64) unfold_ln_kernel<TIN, LN, 3, 64><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
   else unfold_ln_kernel<TIN, LN, 0, 0><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
 }
