@@ -17,6 +17,8 @@
 // picks up (next image's tokens, or zero fill past the end of the matrix) never contribute.
 // TMEM: 2 slots x 256 columns (S at [0,SK), P overlaid at [0,SK/2), O overlaid at [128,192)).
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "common.h"
@@ -167,6 +169,83 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int nvalid, ui
   }
 }
 
+// One query row per thread: row maximum, exponentials, bf16 P written over the consumed S columns of the slot at t_row,
+// f32 row sum returned (the caller issues tcgen05.wait::st).  n16 = score chunks of 16 columns, last_valid = valid columns
+// in the last one.
+__device__ __forceinline__ float softmax_row(uint32_t t_row, int n16, int last_valid, float scale_log2e) {
+  const uint64_t scale2 = pk2(scale_log2e, scale_log2e);
+  float sum;
+  {
+    // Both passes walk the row in 16-column chunks, double-buffered: the next tcgen05.ld is in flight while the
+    // current chunk is reduced / exponentiated.
+    uint32_t ra[16], rb[16];
+    // pass 1: row max
+    float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    {
+      ptx::tmem_ld_x16(t_row, ra);
+      int c = 0;
+#pragma unroll 1
+      for (; c + 2 <= n16 - 1; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+        chunk_max<16, false>(ra, 16, m);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
+        chunk_max<16, false>(rb, 16, m);
+      }
+      if (c + 1 < n16) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+        chunk_max<16, false>(ra, 16, m);
+        ptx::tmem_ld_wait();
+        chunk_max<16, true>(rb, last_valid, m);
+      } else {
+        ptx::tmem_ld_wait();
+        chunk_max<16, true>(ra, last_valid, m);
+      }
+    }
+    const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    const float nm = -mx * scale_log2e;
+    const uint64_t negm2 = pk2(nm, nm);
+    // pass 2: probabilities (bf16) written over the S columns already consumed; fp32 row sum
+    uint64_t sum2[2] = {0ull, 0ull};
+    {
+      uint32_t pk[8];
+      ptx::tmem_ld_x16(t_row, ra);
+      int c = 0;
+#pragma unroll 1
+      for (; c + 2 <= n16 - 1; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+        chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
+        ptx::tmem_st_x8(t_row + c * 8, pk);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
+        chunk_exp<16, false>(rb, 16, scale2, negm2, sum2, pk);
+        ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
+      }
+      if (c + 1 < n16) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
+        chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
+        ptx::tmem_st_x8(t_row + c * 8, pk);
+        ptx::tmem_ld_wait();
+        chunk_exp<16, true>(rb, last_valid, scale2, negm2, sum2, pk);
+        ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
+      } else {
+        ptx::tmem_ld_wait();
+        chunk_exp<16, true>(ra, last_valid, scale2, negm2, sum2, pk);
+        ptx::tmem_st_x8(t_row + c * 8, pk);
+      }
+    }
+    float s0, s1, s2, s3;
+    upk2(sum2[0], s0, s1);
+    upk2(sum2[1], s2, s3);
+    sum = (s0 + s1) + (s2 + s3);
+  }
+  return sum;
+}
+
 __global__ void __launch_bounds__(kThreadsP, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -300,72 +379,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::tc_fence_after();
       float sum = 1.f;
       if (warp_live) {
-        // Both passes walk the row in 16-column chunks, double-buffered: the next tcgen05.ld is in flight while the
-        // current chunk is reduced / exponentiated.
-        uint32_t ra[16], rb[16];
-        // pass 1: row max
-        float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-        {
-          ptx::tmem_ld_x16(t_row, ra);
-          int c = 0;
-#pragma unroll 1
-          for (; c + 2 <= n16 - 1; c += 2) {
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
-            chunk_max<16, false>(ra, 16, m);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
-            chunk_max<16, false>(rb, 16, m);
-          }
-          if (c + 1 < n16) {
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
-            chunk_max<16, false>(ra, 16, m);
-            ptx::tmem_ld_wait();
-            chunk_max<16, true>(rb, last_valid, m);
-          } else {
-            ptx::tmem_ld_wait();
-            chunk_max<16, true>(ra, last_valid, m);
-          }
-        }
-        const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-        const float nm = -mx * p.scale_log2e;
-        const uint64_t negm2 = pk2(nm, nm);
-        // pass 2: probabilities (bf16) written over the S columns already consumed; fp32 row sum
-        uint64_t sum2[2] = {0ull, 0ull};
-        {
-          uint32_t pk[8];
-          ptx::tmem_ld_x16(t_row, ra);
-          int c = 0;
-#pragma unroll 1
-          for (; c + 2 <= n16 - 1; c += 2) {
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
-            chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
-            ptx::tmem_st_x8(t_row + c * 8, pk);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 2) * 16, ra);
-            chunk_exp<16, false>(rb, 16, scale2, negm2, sum2, pk);
-            ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
-          }
-          if (c + 1 < n16) {
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_x16(t_row + (c + 1) * 16, rb);
-            chunk_exp<16, false>(ra, 16, scale2, negm2, sum2, pk);
-            ptx::tmem_st_x8(t_row + c * 8, pk);
-            ptx::tmem_ld_wait();
-            chunk_exp<16, true>(rb, last_valid, scale2, negm2, sum2, pk);
-            ptx::tmem_st_x8(t_row + (c + 1) * 8, pk);
-          } else {
-            ptx::tmem_ld_wait();
-            chunk_exp<16, true>(ra, last_valid, scale2, negm2, sum2, pk);
-            ptx::tmem_st_x8(t_row + c * 8, pk);
-          }
-        }
-        float s0, s1, s2, s3;
-        upk2(sum2[0], s0, s1);
-        upk2(sum2[1], s2, s3);
-        sum = (s0 + s1) + (s2 + s3);
+        sum = softmax_row(t_row, n16, last_valid, p.scale_log2e);
         ptx::tmem_st_wait();
       }
       ptx::tc_fence_before();
@@ -425,6 +439,202 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kIssueWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL variant (EVT_ATTN_PP=1): ONE softmax group of four warps and TWO score buffers in TMEM
+//   S0 [0, 208)  S1 [208, 416)  O [416, 480)            (2 x 208 + 64 = 480 of 512 columns)
+// so that S = Q K^T of item j+1 runs on the tensor pipe while the group exponentiates item j, and O = P V of item j runs
+// under the row-max / exponential passes of item j+1: the group never waits for an MMA in steady state (in the default
+// kernel each group's chain QK -> softmax -> PV -> read-out is serial: 32 % of its time is spent waiting for the two
+// MMAs).  Price: one softmax warp per SM sub-partition instead of two, so the MUFU pipe has no second warp to fill the
+// gaps of the first.  Issue order per item j:  QK(j+1);  wait P(j) -> PV(j).  The tensor pipe executes in issue order,
+// which is what makes the buffer re-use safe: QK(j+2) overwrites the buffer whose P(j) was read by PV(j), issued before it.
+constexpr int kPPThreads = 32 * 6;   // warps 0-3 softmax, 4 TMA producer, 5 MMA issuer
+constexpr int kPPSCols = 208;
+constexpr int kPPOCol = 416;
+
+__global__ void __launch_bounds__(kPPThreads, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kv_bytes = p.SK * 128;
+  const int stage_bytes = kQRows * 128 + 2 * kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * stage_bytes);
+  uint64_t* full = bars;                      // [kMaxStages] producer -> issuer
+  uint64_t* empty = bars + kMaxStages;        // [kMaxStages] issuer (commit) -> producer
+  uint64_t* s_ready = bars + 2 * kMaxStages;  // [2] issuer (commit) -> softmax warps, one per score buffer
+  uint64_t* p_ready = s_ready + 2;            // [1] softmax warps (4 arrivals): P(j) written and O(j-1) read out
+  uint64_t* o_ready = p_ready + 1;            // [1] issuer (commit) -> softmax warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_ready + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a = p.heads * kHD;
+  const int total_units = p.B * p.heads * (p.q_tiles / p.n_mt);
+  const int my_units = (total_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_items = my_units * p.n_mt;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
+    for (int s = 0; s < kMaxStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(&s_ready[0], 1);
+    ptx::mbar_init(&s_ready[1], 1);
+    ptx::mbar_init(p_ready, 4);
+    ptx::mbar_init(o_ready, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer (as in attention_kernel)
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_items; ++j) {
+        const Item it = item_of(p, j);
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        uint8_t* sQ = smem + st * stage_bytes;
+        uint8_t* sK = sQ + kQRows * 128;
+        uint8_t* sV = sK + kv_bytes;
+        const int row0 = it.b * p.S;
+        ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+        ptx::tma_load_2d(sQ, &tmQ, &full[st], it.h * kHD, row0 + it.mt * kQRows);
+        ptx::tma_load_2d(sK, &tmKV, &full[st], a + it.h * kHD, row0);
+        ptx::tma_load_2d(sV, &tmKV, &full[st], 2 * a + it.h * kHD, row0);
+        if (++st == p.n_stages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_items > 0) {
+      const uint32_t idesc_qk = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
+      const uint32_t idesc_pv = ptx::make_idesc(kQRows, kHD, 1, 0, 1);
+      const int nk = p.SK / 16;
+      int st = 0;          // stage of the item whose QK is issued next
+      uint32_t ph = 0;
+      auto issue_qk = [&](int jj) {
+        ptx::mbar_wait(&full[st], ph);
+        ptx::tc_fence_after();
+        const uint32_t sq = ptx::smem_u32(smem + st * stage_bytes);
+        const uint64_t qd = ptx::smem_desc_sw128(sq);
+        const uint64_t kd = ptx::smem_desc_sw128(sq + kQRows * 128);
+        const uint32_t sbuf = tmem_base + (jj & 1) * kPPSCols;
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) ptx::mma_f16_ss(sbuf, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        ptx::mma_commit(&s_ready[jj & 1]);
+        if (++st == p.n_stages) {
+          st = 0;
+          ph ^= 1;
+        }
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_items; ++j) {
+        if (j + 1 < n_items) issue_qk(j + 1);       // runs under the exponentials of item j
+        ptx::mbar_wait(p_ready, j & 1);             // P(j) complete, O(j-1) read out
+        ptx::tc_fence_after();
+        const int stj = j % p.n_stages;
+        const uint32_t sbuf = tmem_base + (j & 1) * kPPSCols;
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(smem + stj * stage_bytes + kQRows * 128 + kv_bytes));
+        for (int k = 0; k < nk; ++k)
+          ptx::mma_f16_ts(tmem_base + kPPOCol, sbuf + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+        ptx::mma_commit(o_ready);
+        ptx::mma_commit(&empty[stj]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps 0..3: thread = query row
+    const int quad = warp;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int n16 = p.SK / 16;
+    const int last_valid = p.S - (n16 - 1) * 16;
+    Item prev = {0, 0, 0};
+    float prev_inv = 0.f;
+    bool prev_live = false;
+    auto read_out_and_store = [&](uint32_t (&o0)[32], uint32_t (&o1)[32]) {
+      const int qrow = prev.mt * kQRows + quad * 32 + lane;
+      if (prev_live && qrow < p.S) {
+        __nv_bfloat16* dst = p.ctx + (static_cast<long long>(prev.b) * p.S + qrow) * p.ldc + prev.h * kHD;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 8) {
+            const uint32_t* r = half == 0 ? &o0[jj] : &o1[jj];
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[0]) * prev_inv, __uint_as_float(r[1]) * prev_inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[2]) * prev_inv, __uint_as_float(r[3]) * prev_inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[4]) * prev_inv, __uint_as_float(r[5]) * prev_inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[6]) * prev_inv, __uint_as_float(r[7]) * prev_inv);
+            o.x = *reinterpret_cast<uint32_t*>(&t0);
+            o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2);
+            o.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(dst + half * 32 + jj) = o;
+          }
+        }
+      }
+    };
+#pragma unroll 1
+    for (int j = 0; j <= n_items; ++j) {
+      Item it = {0, 0, 0};
+      float sum = 1.f;
+      bool live = false;
+      if (j < n_items) {
+        it = item_of(p, j);
+        live = it.mt * kQRows + quad * 32 < p.S;
+        ptx::mbar_wait(&s_ready[j & 1], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        if (live) {
+          sum = softmax_row(lane_base + (j & 1) * kPPSCols, n16, last_valid, p.scale_log2e);
+          ptx::tmem_st_wait();
+        }
+      }
+      // O of the previous item: complete long ago in steady state (its MMAs ran under the passes above)
+      uint32_t o0[32], o1[32];
+      if (j > 0) {
+        ptx::mbar_wait(o_ready, (j - 1) & 1);
+        ptx::tc_fence_after();
+        if (prev_live) {
+          ptx::tmem_ld_x32(lane_base + kPPOCol, o0);
+          ptx::tmem_ld_x32(lane_base + kPPOCol + 32, o1);
+          ptx::tmem_ld_wait();
+        }
+      }
+      if (j < n_items) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_ready);   // P(j) is in TMEM and O(j-1) is in registers: PV(j) may run
+      }
+      if (j > 0) read_out_and_store(o0, o1);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));
+      if (p.head_mask != nullptr && j < n_items) inv *= p.head_mask[it.h];
+      prev = it;
+      prev_inv = inv;
+      prev_live = live;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
@@ -660,6 +870,18 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   }
   const long long units = n_pairs * (p.q_tiles / p.n_mt);
   const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
+  static const bool use_pp = getenv("EVT_ATTN_PP") != nullptr && atoi(getenv("EVT_ATTN_PP")) != 0;
+  if (use_pp && SK <= kPPSCols) {
+    static int pp_dev = -1;
+    if (pp_dev != dev) {
+      EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      pp_dev = dev;
+    }
+    EVT_CUDA(launch_pdl(attention_pp_kernel, dim3(grid), dim3(kPPThreads), smem, stream,
+                        pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
+    EVT_LAUNCH_CHECK("attention_pp_kernel");
+    return EVT_OK;
+  }
   EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;
