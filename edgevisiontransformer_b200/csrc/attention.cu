@@ -454,12 +454,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // MMAs).  Price: one softmax warp per SM sub-partition instead of two, so the MUFU pipe has no second warp to fill the
 // gaps of the first.  Issue order per item j:  QK(j+1);  wait P(j) -> PV(j).  The tensor pipe executes in issue order,
 // which is what makes the buffer re-use safe: QK(j+2) overwrites the buffer whose P(j) was read by PV(j), issued before it.
-constexpr int kPPThreads = 32 * 6;   // warps 0-3 softmax, 4 TMA producer, 5 MMA issuer
 constexpr int kPPSCols = 208;
 constexpr int kPPOCol = 416;
+constexpr int kPPMaxHalfChunks = 7;  // 13 score chunks of 16 columns split 7 + 6 between the two threads of a row
 
-__global__ void __launch_bounds__(kPPThreads, 1)
+// HALVES = 1: one thread per query row (four softmax warps).  HALVES = 2: two threads per row (eight softmax warps, the
+// second MUFU client per sub-partition back): thread h of a row owns the score chunks [h * 7, ...) and the context columns
+// [32 h, 32 h + 32).  Row maximum and row sum are exchanged through shared memory with a 64-thread named barrier per
+// lane quadrant; because P overlays S, a thread keeps its bf16 P half in registers until BOTH threads have consumed
+// their score columns (the second barrier) and only then writes it to TMEM.
+template <int HALVES>
+__global__ void __launch_bounds__(32 * (4 * HALVES + 2), 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  constexpr int kSoftWarps = 4 * HALVES, kProd = kSoftWarps, kIssue = kSoftWarps + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_bytes = p.SK * 128;
@@ -468,9 +475,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* full = bars;                      // [kMaxStages] producer -> issuer
   uint64_t* empty = bars + kMaxStages;        // [kMaxStages] issuer (commit) -> producer
   uint64_t* s_ready = bars + 2 * kMaxStages;  // [2] issuer (commit) -> softmax warps, one per score buffer
-  uint64_t* p_ready = s_ready + 2;            // [1] softmax warps (4 arrivals): P(j) written and O(j-1) read out
+  uint64_t* p_ready = s_ready + 2;            // [1] softmax warps: P(j) written and O(j-1) read out
   uint64_t* o_ready = p_ready + 1;            // [1] issuer (commit) -> softmax warps
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_ready + 1);
+  float* xch = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // [2 (max | sum)][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -479,7 +487,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int my_units = (total_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int n_items = my_units * p.n_mt;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kProd && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
     for (int s = 0; s < kMaxStages; ++s) {
@@ -488,11 +496,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     ptx::mbar_init(&s_ready[0], 1);
     ptx::mbar_init(&s_ready[1], 1);
-    ptx::mbar_init(p_ready, 4);
+    ptx::mbar_init(p_ready, kSoftWarps);
     ptx::mbar_init(o_ready, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 5) ptx::tmem_alloc<512>(tmem_ptr);
+  if (warp == kIssue) ptx::tmem_alloc<512>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -500,7 +508,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
 
-  if (warp == 4) {
+  if (warp == kProd) {
     // ------------------------------------------------------------ TMA producer (as in attention_kernel)
     if (lane == 0) {
       int st = 0;
@@ -522,7 +530,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kIssue) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_items > 0) {
       const uint32_t idesc_qk = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
@@ -560,37 +568,22 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax warps 0..3: thread = query row
-    const int quad = warp;
+    // ------------------------------------------------------------ softmax warps: thread = (query row, half)
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n16 = p.SK / 16;
     const int last_valid = p.S - (n16 - 1) * 16;
+    const int c_split = HALVES == 2 ? (n16 + 1) / 2 : n16;
+    const int c0 = half == 0 ? 0 : c_split, c1 = half == 0 ? c_split : n16;
+    constexpr int kOC = 64 / HALVES;               // context columns of this thread
+    float* xmax = xch;
+    float* xsum = xch + 2 * 128;
+    const uint64_t scale2 = pk2(p.scale_log2e, p.scale_log2e);
     Item prev = {0, 0, 0};
     float prev_inv = 0.f;
     bool prev_live = false;
-    auto read_out_and_store = [&](uint32_t (&o0)[32], uint32_t (&o1)[32]) {
-      const int qrow = prev.mt * kQRows + quad * 32 + lane;
-      if (prev_live && qrow < p.S) {
-        __nv_bfloat16* dst = p.ctx + (static_cast<long long>(prev.b) * p.S + qrow) * p.ldc + prev.h * kHD;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 8) {
-            const uint32_t* r = half == 0 ? &o0[jj] : &o1[jj];
-            uint4 o;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[0]) * prev_inv, __uint_as_float(r[1]) * prev_inv);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[2]) * prev_inv, __uint_as_float(r[3]) * prev_inv);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[4]) * prev_inv, __uint_as_float(r[5]) * prev_inv);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[6]) * prev_inv, __uint_as_float(r[7]) * prev_inv);
-            o.x = *reinterpret_cast<uint32_t*>(&t0);
-            o.y = *reinterpret_cast<uint32_t*>(&t1);
-            o.z = *reinterpret_cast<uint32_t*>(&t2);
-            o.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(dst + half * 32 + jj) = o;
-          }
-        }
-      }
-    };
 #pragma unroll 1
     for (int j = 0; j <= n_items; ++j) {
       Item it = {0, 0, 0};
@@ -602,18 +595,71 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ptx::mbar_wait(&s_ready[j & 1], (j >> 1) & 1);
         ptx::tc_fence_after();
         if (live) {
-          sum = softmax_row(lane_base + (j & 1) * kPPSCols, n16, last_valid, p.scale_log2e);
-          ptx::tmem_st_wait();
+          if constexpr (HALVES == 1) {
+            sum = softmax_row(lane_base + (j & 1) * kPPSCols, n16, last_valid, p.scale_log2e);
+            ptx::tmem_st_wait();
+          } else {
+            const uint32_t t_row = lane_base + (j & 1) * kPPSCols;
+            uint32_t buf[2][16];
+            // pass 1: maximum over this thread's chunks
+            float m[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+            if (c0 < c1) ptx::tmem_ld_x16(t_row + c0 * 16, buf[0]);
+#pragma unroll
+            for (int i = 0; i < kPPMaxHalfChunks; ++i) {
+              const int c = c0 + i;
+              if (c < c1) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < c1) ptx::tmem_ld_x16(t_row + (c + 1) * 16, buf[(i + 1) & 1]);
+                if (c == n16 - 1) chunk_max<16, true>(buf[i & 1], last_valid, m);
+                else chunk_max<16, false>(buf[i & 1], 16, m);
+              }
+            }
+            float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+            xmax[half * 128 + row_in_tile] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+            mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row_in_tile]);
+            const float nm = -mx * p.scale_log2e;
+            const uint64_t negm2 = pk2(nm, nm);
+            // pass 2: exponentials of this thread's chunks; the bf16 P half stays in registers
+            uint64_t sum2[2] = {0ull, 0ull};
+            uint32_t pk[kPPMaxHalfChunks][8];
+            if (c0 < c1) ptx::tmem_ld_x16(t_row + c0 * 16, buf[0]);
+#pragma unroll
+            for (int i = 0; i < kPPMaxHalfChunks; ++i) {
+              const int c = c0 + i;
+              if (c < c1) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < c1) ptx::tmem_ld_x16(t_row + (c + 1) * 16, buf[(i + 1) & 1]);
+                if (c == n16 - 1) chunk_exp<16, true>(buf[i & 1], last_valid, scale2, negm2, sum2, pk[i]);
+                else chunk_exp<16, false>(buf[i & 1], 16, scale2, negm2, sum2, pk[i]);
+              }
+            }
+            float s0, s1, s2, s3;
+            upk2(sum2[0], s0, s1);
+            upk2(sum2[1], s2, s3);
+            const float part = (s0 + s1) + (s2 + s3);
+            xsum[half * 128 + row_in_tile] = part;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // both threads of the row are done reading S
+            sum = part + xsum[(half ^ 1) * 128 + row_in_tile];
+#pragma unroll
+            for (int i = 0; i < kPPMaxHalfChunks; ++i)
+              if (c0 + i < c1) ptx::tmem_st_x8(t_row + (c0 + i) * 8, pk[i]);
+            ptx::tmem_st_wait();
+          }
         }
       }
       // O of the previous item: complete long ago in steady state (its MMAs ran under the passes above)
-      uint32_t o0[32], o1[32];
+      uint32_t o[kOC];
       if (j > 0) {
         ptx::mbar_wait(o_ready, (j - 1) & 1);
         ptx::tc_fence_after();
         if (prev_live) {
-          ptx::tmem_ld_x32(lane_base + kPPOCol, o0);
-          ptx::tmem_ld_x32(lane_base + kPPOCol + 32, o1);
+          if constexpr (HALVES == 1) {
+            ptx::tmem_ld_x32(lane_base + kPPOCol, reinterpret_cast<uint32_t(&)[32]>(o[0]));
+            ptx::tmem_ld_x32(lane_base + kPPOCol + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
+          } else {
+            ptx::tmem_ld_x32(lane_base + kPPOCol + half * 32, reinterpret_cast<uint32_t(&)[32]>(o[0]));
+          }
           ptx::tmem_ld_wait();
         }
       }
@@ -622,7 +668,25 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_ready);   // P(j) is in TMEM and O(j-1) is in registers: PV(j) may run
       }
-      if (j > 0) read_out_and_store(o0, o1);
+      if (j > 0) {
+        const int qrow = prev.mt * kQRows + row_in_tile;
+        if (prev_live && qrow < p.S) {
+          __nv_bfloat16* dst = p.ctx + (static_cast<long long>(prev.b) * p.S + qrow) * p.ldc + prev.h * kHD + (HALVES == 2 ? half * 32 : 0);
+#pragma unroll
+          for (int jj = 0; jj < kOC; jj += 8) {
+            uint4 v;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[jj]) * prev_inv, __uint_as_float(o[jj + 1]) * prev_inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[jj + 2]) * prev_inv, __uint_as_float(o[jj + 3]) * prev_inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[jj + 4]) * prev_inv, __uint_as_float(o[jj + 5]) * prev_inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[jj + 6]) * prev_inv, __uint_as_float(o[jj + 7]) * prev_inv);
+            v.x = *reinterpret_cast<uint32_t*>(&t0);
+            v.y = *reinterpret_cast<uint32_t*>(&t1);
+            v.z = *reinterpret_cast<uint32_t*>(&t2);
+            v.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(dst + jj) = v;
+          }
+        }
+      }
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));
       if (p.head_mask != nullptr && j < n_items) inv *= p.head_mask[it.h];
@@ -634,7 +698,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kIssue) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
@@ -870,15 +934,19 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   }
   const long long units = n_pairs * (p.q_tiles / p.n_mt);
   const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
-  static const bool use_pp = getenv("EVT_ATTN_PP") != nullptr && atoi(getenv("EVT_ATTN_PP")) != 0;
-  if (use_pp && SK <= kPPSCols) {
+  static const int pp_mode = getenv("EVT_ATTN_PP") != nullptr ? atoi(getenv("EVT_ATTN_PP")) : 0;  // 1 / 2 threads per row
+  if (pp_mode != 0 && SK <= kPPSCols && smem + 2048 <= max_smem) {
     static int pp_dev = -1;
     if (pp_dev != dev) {
-      EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       pp_dev = dev;
     }
-    EVT_CUDA(launch_pdl(attention_pp_kernel, dim3(grid), dim3(kPPThreads), smem, stream,
-                        pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
+    const bool pdl = pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD);
+    if (pp_mode == 2)
+      EVT_CUDA(launch_pdl(attention_pp_kernel<2>, dim3(grid), dim3(32 * 10), smem + 2048, stream, pdl, tmQ, tmKV, p));
+    else
+      EVT_CUDA(launch_pdl(attention_pp_kernel<1>, dim3(grid), dim3(32 * 6), smem + 2048, stream, pdl, tmQ, tmKV, p));
     EVT_LAUNCH_CHECK("attention_pp_kernel");
     return EVT_OK;
   }
