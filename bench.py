@@ -288,8 +288,8 @@ def main():
                 "alone": {"achieved": alone, "peak": pk["tf_burst"], "frac": alone / pk["tf_burst"], "ms_per_launch": alone_ms,
                           "peak_source": pk["src"] + " (burst: kernel timed alone)"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, from the committed
-                # ncu --set full capture profiles/r01_layer_ncu_full.md: 0.323 GB read + 1.190 GB written (algorithmic: A 0.310 + out 1.239 + W 0.005 GB)
-                "traffic": 1.513e9 if (M, inter, d) == (201728, 3072, 768) else None,
+                # ncu --set full capture profiles/r01_layer_ncu_full.md: 0.323 GB read + 1.187 GB written (algorithmic: A 0.310 + out 1.239 + W 0.005 GB)
+                "traffic": 1.510e9 if (M, inter, d) == (201728, 3072, 768) else None,
                 "model_frac_sustained": value / n_gpus * GFLOP_PER_IMG[args.workload] / 1e3 / pk["tf_sustained"]}
         del a, w, b, o
 
