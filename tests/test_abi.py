@@ -45,6 +45,12 @@ def test_no_silent_cpu_fallback(lib):
         B200ViTForImageClassification(B200ViTConfig(), {}, device="cpu")
     rc = lib.evt_gemm_bias_act(None, 8, None, 8, None, None, 0, 0, 0, None, 0, 8, 0, 0, 0, 1, 1, 1, 0, None)
     assert rc != 0
+    from edgevisiontransformer_b200.modeling_swin import B200SwinForImageClassification
+    with pytest.raises(RuntimeError):
+        B200SwinForImageClassification({}, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], embed_dim=96, device="cpu")
+    with pytest.raises(RuntimeError):
+        ops.window_attention(torch.zeros(49, 288, dtype=torch.bfloat16), torch.zeros(1, 3, 64, 56), 1, 3)
+    assert lib.evt_window_attention_fwd(None, 0, None, 0, None, 1, 1, 49, 3, 32, 0.0, None) != 0
 
 
 def test_product_does_not_import_oracle():
