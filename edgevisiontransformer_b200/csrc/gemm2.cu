@@ -30,7 +30,8 @@ constexpr int kEpiWarpsAct = EVT_EPI_WARPS_ACT;  // epilogue warps of the bf16-o
 // EW = epilogue warps per CTA (8, or 16 = 4 per TMEM lane quadrant with one 64-column chunk each).  16 was tried for the
 // FC1 + GELU kernel (-DEVT_EPI_WARPS_ACT=16) on the theory that the epilogue's latency per tile holds up the accumulator
 // hand-off: it measured SLOWER (FC1 0.944 vs 0.912 ms in the step, 1101 vs 1248 TFLOP/s alone) -- 576 threads leave 96
-// registers per thread (the unrolled GELU loses its interleaving) and the extra staging costs a pipeline stage.  Default 8.
+// registers per thread (the unrolled GELU loses its interleaving) and the extra staging costs a pipeline stage; 12 (three
+// groups, rotating) measured equal within noise.  Default 8.
 template <int BN, int EW>
 struct Cfg2 {
   static constexpr int kABytes = BM * kStageRowBytes;
@@ -173,14 +174,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue warps 0..7 (both CTAs, own 128 rows)
     const int quad = warp & 3;
-    const int grp = warp >> 2;
     uint8_t* stg = staging + warp * kStgBytes * kStgBufs;
     int stg_sel = 0;
     int as = 0;
     uint32_t aphase = 0;
+    // With a group count that does not divide the chunk count (12 warps = 3 groups, 4 chunks of 64 columns) the group that
+    // takes two chunks rotates from tile to tile, so every warp does 4 chunks per 3 tiles.
+    constexpr int kGroups = EW / 4;
+    constexpr bool kRotate = ((BN / (OUT_F32 ? 32 : 64)) % kGroups) != 0;
+    const int grp0 = warp >> 2;
+    int rot = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + quad * 32;
       const int nt0 = (tile % p.tiles_n) * BN;
+      int grp = grp0;
+      if (kRotate) {
+        grp = grp0 + rot;
+        if (grp >= kGroups) grp -= kGroups;
+        if (++rot == kGroups) rot = 0;
+      }
       prefetch_bias<BN, OUT_F32, EW / 4>(p, grp, lane, nt0);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
