@@ -32,6 +32,15 @@ class ModelSpec(C.Structure):
     ]
 
 
+class ForwardOpts(C.Structure):
+    """evt_forward_opts (include/evt.h): pixel storage type, u8 normalisation, head mask, per-layer context capture."""
+    _fields_ = [("pixel_dtype", C.c_int), ("pixel_scale", C.c_float * 3), ("pixel_bias", C.c_float * 3),
+                ("head_mask", C.c_void_p), ("head_mask_ld", C.c_int), ("ctx_out", C.POINTER(C.c_void_p))]
+
+
+PIX_F32, PIX_BF16, PIX_U8 = 0, 1, 2
+
+
 class TensorView(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4)]
 
@@ -66,6 +75,7 @@ SIGNATURES = {
     "evt_model_load_weights": (_i, [_p, C.POINTER(TensorView), _i, _p]),
     "evt_model_workspace_bytes": (_i, [_p, _i, C.POINTER(_sz)]),
     "evt_model_forward": (_i, [_p, _p, _i, _p, _p, _sz, _p]),
+    "evt_model_forward_ex": (_i, [_p, _p, C.POINTER(ForwardOpts), _i, _p, _p, _sz, _p]),
     "evt_model_forward_embedded": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
     "evt_unfold_ln_nhwc": (_i, [_p, _i, _p, _i64, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p]),
     "evt_performer_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),

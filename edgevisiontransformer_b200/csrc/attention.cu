@@ -445,6 +445,298 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Round-2 kernel.  Same arithmetic and TMEM slot layout as attention_kernel above (the softmax code is shared); what
+// changed is everything around it, driven by the round-1 warp-sample profile (56 % of the softmax warps' time was spent
+// WAITING, 31 % for O = P V alone, although the tensor pipe was 25 % busy):
+//   * the single issuer thread was the bottleneck: written under `lane == 0`, every tcgen05.mma was wrapped by ptxas in an
+//     ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the descriptor arithmetic ran on per-thread registers (~110 cycles per MMA
+//     issued, 3650 per item).  The roles are now chosen with elect.sync (uniform datapath, MMAs issue back to back), and
+//     S = Q K^T and O = P V are issued by TWO warps, so a P that is ready never queues behind the other group's slot wait.
+//   * K and V of an (image, head) pair are loaded ONCE for both query tiles (ring of n_kv pair stages, Q tiles in their
+//     own 2-deep ring -- one per softmax group): 138 -> 85 KB of L2 -> SM traffic per pair.
+//   * the context tile leaves through a 128B-swizzled staging tile and a 3-D TMA store (box = 32 rows of one image, rows
+//     past the sequence end clipped by the tensor map) instead of 32 scattered 16-byte stores per instruction, whose
+//     source registers held the warp for 13 % of its time.
+constexpr int kQKWarp = 9;
+constexpr int kPVWarp = 10;
+constexpr int kThreads2 = 32 * (kSoftmaxWarps + 3);
+constexpr int kQTileBytes = kQRows * 128;
+constexpr int kStgWarpBytes = 32 * 128;
+constexpr int kMaxKV = 4;
+
+struct Attn2Params {
+  const float* head_mask;
+  int S, SK, heads, B;
+  int n_mt;      // query tiles per work unit (q_tiles, or 1 when the tiles of a pair are split across CTAs)
+  int q_tiles;   // query tiles per (image, head)
+  int n_kv;      // K/V ring depth
+  float scale_log2e;
+};
+
+struct Unit {
+  int b, h, mt0;  // mt0: the tile of a split-mode unit (else 0)
+};
+__device__ __forceinline__ Unit unit_of(const Attn2Params& p, int ql) {
+  const int unit = blockIdx.x + ql * gridDim.x;
+  Unit u;
+  int pair = unit;
+  u.mt0 = 0;
+  if (p.n_mt != p.q_tiles) {
+    pair = unit / p.q_tiles;
+    u.mt0 = unit - pair * p.q_tiles;
+  }
+  u.b = pair / p.heads;
+  u.h = pair - u.b * p.heads;
+  return u;
+}
+// query tile of item s (0 .. n_mt-1) of unit ql: the order flips on every other unit so that both softmax groups see
+// full and ragged tiles
+__device__ __forceinline__ int tile_of(const Attn2Params& p, const Unit& u, int ql, int s) {
+  if (p.n_mt != p.q_tiles) return u.mt0;
+  return p.n_mt == 2 ? (s ^ (ql & 1)) : s;
+}
+
+__global__ void __launch_bounds__(kThreads2, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                  const __grid_constant__ CUtensorMap tmO, const Attn2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kv_bytes = p.SK * 128;
+  uint8_t* kv_ring = smem;                                   // n_kv x (K | V)
+  uint8_t* q_ring = smem + p.n_kv * 2 * kv_bytes;            // 2 x Q tile, one per softmax group
+  uint8_t* staging = q_ring + 2 * kQTileBytes;               // 8 x 4 KB context staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSoftmaxWarps * kStgWarpBytes);
+  uint64_t* kv_full = bars;                   // [kMaxKV] producer -> issuers
+  uint64_t* kv_empty = bars + kMaxKV;         // [kMaxKV] PV issuer (n_mt commits) -> producer
+  uint64_t* q_full = bars + 2 * kMaxKV;       // [2] producer -> QK issuer
+  uint64_t* q_empty = q_full + 2;             // [2] QK issuer (commit) -> producer
+  uint64_t* s_ready = q_empty + 2;            // [2] QK issuer (commit) -> softmax group
+  uint64_t* p_ready = s_ready + 2;            // [2] softmax group (4 warps) -> PV issuer
+  uint64_t* o_ready = p_ready + 2;            // [2] PV issuer (commit) -> softmax group
+  uint64_t* slot_free = o_ready + 2;          // [2] softmax group (4 warps) -> QK issuer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a = p.heads * kHD;
+  const int total_units = p.B * p.heads * (p.q_tiles / p.n_mt);
+  const int my_units = (total_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_items = my_units * p.n_mt;
+
+  if (warp == kProdWarp && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
+    ptx::prefetch_tmap(&tmO);
+    for (int s = 0; s < kMaxKV; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], p.n_mt);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&q_full[s], 1);
+      ptx::mbar_init(&q_empty[s], 1);
+      ptx::mbar_init(&s_ready[s], 1);
+      ptx::mbar_init(&p_ready[s], 4);
+      ptx::mbar_init(&o_ready[s], 1);
+      ptx::mbar_init(&slot_free[s], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kQKWarp) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();  // qkv (previous kernel's output) is complete from here on
+
+  if (warp == kProdWarp) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int kst = 0;
+      uint32_t kph = 0;
+      int j = 0;
+      for (int ql = 0; ql < my_units; ++ql) {
+        const Unit u = unit_of(p, ql);
+        const int row0 = u.b * p.S;
+        ptx::mbar_wait(&kv_empty[kst], kph ^ 1);
+        uint8_t* sK = kv_ring + kst * 2 * kv_bytes;
+        ptx::mbar_arrive_expect_tx(&kv_full[kst], 2 * kv_bytes);
+        ptx::tma_load_2d(sK, &tmKV, &kv_full[kst], a + u.h * kHD, row0);
+        ptx::tma_load_2d(sK + kv_bytes, &tmKV, &kv_full[kst], 2 * a + u.h * kHD, row0);
+        for (int s = 0; s < p.n_mt; ++s, ++j) {
+          const int g = j & 1;
+          ptx::mbar_wait(&q_empty[g], ((j >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&q_full[g], kQTileBytes);
+          ptx::tma_load_2d(q_ring + g * kQTileBytes, &tmQ, &q_full[g], u.h * kHD, row0 + tile_of(p, u, ql, s) * kQRows);
+        }
+        if (++kst == p.n_kv) {
+          kst = 0;
+          kph ^= 1;
+        }
+      }
+    }
+  } else if (warp == kQKWarp) {
+    // ------------------------------------------------------------ S = Q K^T issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc_qk = ptx::make_idesc(kQRows, p.SK, 1, 0, 0);
+      int kst = 0;
+      uint32_t kph = 0;
+      int j = 0;
+      for (int ql = 0; ql < my_units; ++ql) {
+        ptx::mbar_wait(&kv_full[kst], kph);
+        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(kv_ring + kst * 2 * kv_bytes));
+        for (int s = 0; s < p.n_mt; ++s, ++j) {
+          const int g = j & 1;
+          const uint32_t ph = (j >> 1) & 1;
+          ptx::mbar_wait(&q_full[g], ph);
+          ptx::mbar_wait(&slot_free[g], ph ^ 1);
+          ptx::tc_fence_after();
+          const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(q_ring + g * kQTileBytes));
+          const uint32_t slot = tmem_base + g * kSlotCols;
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) ptx::mma_f16_ss(slot, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+          ptx::mma_commit(&s_ready[g]);
+          ptx::mma_commit(&q_empty[g]);  // the Q tile can be replaced as soon as these MMAs have read it
+        }
+        if (++kst == p.n_kv) {
+          kst = 0;
+          kph ^= 1;
+        }
+      }
+    }
+  } else if (warp == kPVWarp) {
+    // ------------------------------------------------------------ O = P V issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc_pv = ptx::make_idesc(kQRows, kHD, 1, 0, 1);
+      const int nk = p.SK / 16;
+      int kst = 0;
+      uint32_t kph = 0;
+      int j = 0;
+      for (int ql = 0; ql < my_units; ++ql) {
+        ptx::mbar_wait(&kv_full[kst], kph);  // complete long ago (S of this unit exists); taken for the memory ordering
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(kv_ring + kst * 2 * kv_bytes + kv_bytes));
+        for (int s = 0; s < p.n_mt; ++s, ++j) {
+          const int g = j & 1;
+          ptx::mbar_wait(&p_ready[g], (j >> 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t slot = tmem_base + g * kSlotCols;
+          // P from TMEM (8 columns per K = 16), V MN-major (2048 B per step)
+          for (int k = 0; k < nk; ++k)
+            ptx::mma_f16_ts(slot + kOCol, slot + 8 * k, vd + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+          ptx::mma_commit(&o_ready[g]);
+          ptx::mma_commit(&kv_empty[kst]);  // n_mt arrivals release K and V of the unit
+        }
+        if (++kst == p.n_kv) {
+          kst = 0;
+          kph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax groups
+    const int grp = warp >> 2;
+    const int quad = warp & 3;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * kSlotCols;
+    const int n16 = p.SK / 16;                    // 16-column score chunks; only the last one can hold masked keys
+    const int last_valid = p.S - (n16 - 1) * 16;  // valid columns in it (1..16)
+    uint8_t* stg = staging + warp * kStgWarpBytes;
+    uint8_t* stg_row = stg + lane * 128;
+    const int sw = lane & 7;
+    // This group's items are j = grp, grp + 2, ...: unit ql = j / n_mt advances by dql per iteration.  (b, h) follow
+    // incrementally -- two integer divisions per item were 11 % of the softmax warps' instructions in round 1.
+    const int dql = p.n_mt == 2 ? 1 : 2;
+    const int step_pairs = dql * static_cast<int>(gridDim.x);
+    const int db = step_pairs / p.heads, dh = step_pairs - db * p.heads;
+    const bool split = p.n_mt != p.q_tiles;
+    int ql = p.n_mt == 2 ? 0 : grp;
+    Unit u = unit_of(p, ql);
+#pragma unroll 1
+    for (int j = grp; j < n_items; j += 2, ql += dql) {
+      const uint32_t ph = (j >> 1) & 1;
+      if (j != grp) {
+        if (split) {
+          u = unit_of(p, ql);
+        } else {
+          u.h += dh;
+          u.b += db;
+          if (u.h >= p.heads) {
+            u.h -= p.heads;
+            ++u.b;
+          }
+        }
+      }
+      const int mt = tile_of(p, u, ql, p.n_mt == 2 ? grp : 0);
+      const int qrow0 = mt * kQRows + quad * 32;
+      const bool warp_live = qrow0 < p.S;  // rows 224..255 of the second tile when S = 197: nothing to do
+      float hm = 1.f;
+      if (p.head_mask != nullptr) hm = p.head_mask[u.h];
+      ptx::mbar_wait(&s_ready[grp], ph);
+      ptx::tc_fence_after();
+      float sum = 1.f;
+      if (warp_live) {
+        sum = softmax_row(t_row, n16, last_valid, p.scale_log2e);
+        ptx::tmem_st_wait();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_ready[grp]);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));  // sum >= 1 (the max contributes 2^0)
+      inv *= hm;
+      if (warp_live && ptx::elect_one()) ptx::bulk_wait_read<0>();  // the previous context tile has left the staging buffer
+      ptx::mbar_wait(&o_ready[grp], ph);
+      ptx::tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (warp_live) {
+        ptx::tmem_ld_x32(t_row + kOCol, o0);
+        ptx::tmem_ld_x32(t_row + kOCol + 32, o1);
+        ptx::tmem_ld_wait();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&slot_free[grp]);  // the slot can take the next S while we convert and store
+      if (warp_live) {
+        // O / sum -> bf16, row per thread into the 128B-swizzled staging tile (16-byte piece i of row r at piece i ^ (r & 7))
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 8) {
+            const uint32_t* r = half == 0 ? &o0[jj] : &o1[jj];
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+            o.x = *reinterpret_cast<uint32_t*>(&t0);
+            o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2);
+            o.w = *reinterpret_cast<uint32_t*>(&t3);
+            const int piece = half * 4 + (jj >> 3);
+            *reinterpret_cast<uint4*>(stg_row + ((piece ^ sw) << 4)) = o;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (ptx::elect_one()) {
+          ptx::tma_store_3d(&tmO, stg, u.h * kHD, qrow0, u.b);  // rows >= S of the image are clipped by the tensor map
+          ptx::bulk_commit();
+        }
+      }
+    }
+    if (ptx::elect_one()) ptx::bulk_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kQKWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+#ifdef EVT_EXPERIMENTAL
 // ------------------------------------------------------------------------------------------------------------
 // EXPERIMENTAL variant (EVT_ATTN_PP=1): ONE softmax group of four warps and TWO score buffers in TMEM
 //   S0 [0, 208)  S1 [208, 416)  O [416, 480)            (2 x 208 + 64 = 480 of 512 columns)
@@ -705,6 +997,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
+#endif  // EVT_EXPERIMENTAL
+
 // ------------------------------------------------------------------------------------------------------------
 // tf32 accuracy mode: Q, K, V and the context are fp32 in HBM; the tensor core reads them as tf32 (kind::tf32,
 // K = 8 per MMA) and accumulates in fp32.  A 64-float head row is two 128-byte swizzle atoms, so Q and K are
@@ -934,6 +1228,38 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   }
   const long long units = n_pairs * (p.q_tiles / p.n_mt);
   const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
+  static const bool use_v1 = getenv("EVT_ATTN_V1") != nullptr && atoi(getenv("EVT_ATTN_V1")) != 0;  // round-1 kernel, for A/B timing
+  if (!use_v1) {
+    CUtensorMap tmO;
+    rc = make_tmap_3d_rows(&tmO, ctx, 2, static_cast<uint64_t>(heads) * kHD, static_cast<uint64_t>(S), static_cast<uint64_t>(B),
+                           static_cast<uint64_t>(ldc), 32, kHD);
+    if (rc != EVT_OK) return rc;
+    Attn2Params q;
+    q.head_mask = head_mask;
+    q.S = S;
+    q.SK = SK;
+    q.heads = heads;
+    q.B = B;
+    q.n_mt = p.n_mt;
+    q.q_tiles = p.q_tiles;
+    q.scale_log2e = p.scale_log2e;
+    const int fixed = 1024 + 2 * kQTileBytes + kSoftmaxWarps * kStgWarpBytes + (2 * kMaxKV + 12) * 8 + 16;
+    int n_kv = (max_smem - fixed) / (2 * SK * 128);
+    if (n_kv > kMaxKV) n_kv = kMaxKV;
+    if (n_kv < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two K/V stages");
+    q.n_kv = n_kv;
+    const int smem2 = fixed + n_kv * 2 * SK * 128;
+    static int dev2 = -1;
+    if (dev2 != dev) {
+      EVT_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      dev2 = dev;
+    }
+    EVT_CUDA(launch_pdl(attention2_kernel, dim3(grid), dim3(kThreads2), smem2, stream,
+                        pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, tmO, q));
+    EVT_LAUNCH_CHECK("attention2_kernel");
+    return EVT_OK;
+  }
+#ifdef EVT_EXPERIMENTAL
   static const int pp_mode = getenv("EVT_ATTN_PP") != nullptr ? atoi(getenv("EVT_ATTN_PP")) : 0;  // 1 / 2 threads per row
   if (pp_mode != 0 && SK <= kPPSCols && smem + 2048 <= max_smem) {
     static int pp_dev = -1;
@@ -950,6 +1276,7 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
     EVT_LAUNCH_CHECK("attention_pp_kernel");
     return EVT_OK;
   }
+#endif  // EVT_EXPERIMENTAL
   EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
   EVT_LAUNCH_CHECK("attention_kernel");
   return EVT_OK;

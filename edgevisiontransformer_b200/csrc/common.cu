@@ -114,6 +114,26 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
   return EVT_OK;
 }
 
+int make_tmap_3d_rows(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t batch,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(EVT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(EVT_ERR_INVALID, "TMA base pointer not 16-byte aligned");
+  if ((ld * elem_bytes) % 16 != 0) return fail(EVT_ERR_INVALID, "TMA leading dimension not a multiple of 16 bytes");
+  if (box_cols * elem_bytes != 128 || box_rows > 256 || box_rows == 0)
+    return fail(EVT_ERR_INVALID, "TMA box must be 128 bytes wide and at most 256 rows");
+  if (elem_bytes != 2) return fail(EVT_ERR_INVALID, "3-D TMA map: bf16 only");
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * static_cast<uint64_t>(elem_bytes), rows * ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EVT_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
+  return EVT_OK;
+}
+
 }  // namespace evt
 
 extern "C" {

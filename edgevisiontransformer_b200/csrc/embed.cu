@@ -14,13 +14,42 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// One thread = 8 consecutive pixels of one image row (32 B in, 16 B out).  Thread order follows the
-// input (b, c, y, x8) so reads are perfectly coalesced; writes are full 16-byte pieces of patch rows.
-// Patch p of image b lands in row  b * row_stride + row_off + p  (row_stride = patches, row_off = 0: dense patch matrix;
-// row_stride = tokens, row_off = number of prefix tokens: one row per TOKEN, so the embedding GEMM's output rows are the
-// rows of the residual stream and its epilogue can be the TMA reduce-add).
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ cols,
-                                                     int B, int H, int W, int P, long long total, int row_stride, int row_off) {
+// One thread = 8 consecutive pixels of one image row (32 / 16 / 8 B in for f32 / bf16 / u8 pixels, 16 B of bf16 or 32 B of
+// tf32-rounded f32 out).  Thread order follows the input (b, c, y, x8) so reads are perfectly coalesced; writes are full
+// 16-byte pieces of patch rows.  Patch p of image b lands in row  b * row_stride + row_off + p  (row_stride = patches,
+// row_off = 0: dense patch matrix; row_stride = tokens, row_off = number of prefix tokens: one row per TOKEN, so the
+// embedding GEMM's output rows are the rows of the residual stream and its epilogue can be the TMA reduce-add).
+// The pixel type conversion is fused here (the C ABI takes f32, bf16 or u8 pixels): u8 pixels are normalised on the fly,
+// value = pixel * scale[c] + bias[c]  (= (pixel / 255 - mean[c]) / std[c], the torchvision Normalize the reference's
+// data loaders apply, deit_pruning/src/utils.py:118-133), which cuts the host -> device bytes of the e2e path by 4x.
+struct PixAffine {
+  float scale[3], bias[3];
+};
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void load8(const uint8_t* p, float (&v)[8]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = static_cast<float>((a.x >> (8 * i)) & 0xffu);
+    v[4 + i] = static_cast<float>((a.y >> (8 * i)) & 0xffu);
+  }
+}
+template <typename TIN, bool OUT_BF16, bool AFFINE>
+__global__ void __launch_bounds__(256) im2col_kernel(const TIN* __restrict__ px, void* __restrict__ cols_, int B, int H, int W,
+                                                     int P, long long total, int row_stride, int row_off, const PixAffine af) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -32,43 +61,30 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ p
   r /= H;
   const int c = static_cast<int>(r % 3);
   const int b = static_cast<int>(r / 3);
-  const float4 v0 = *reinterpret_cast<const float4*>(px + t * 8);
-  const float4 v1 = *reinterpret_cast<const float4*>(px + t * 8 + 4);
+  float v[8];
+  load8(px + t * 8, v);
+  if (AFFINE) {
+    const float sc = af.scale[c], bi = af.bias[c];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc, bi);
+  }
   const int x = x8 * 8;
   const int py = y / P, i = y % P, pxi = x / P, j = x % P;
   const int gw = W / P;
   const long long row = static_cast<long long>(b) * row_stride + row_off + py * gw + pxi;
   const int k = (c * P + i) * P + j;
-  uint4 o;
-  o.x = pack_bf16(v0.x, v0.y);
-  o.y = pack_bf16(v0.z, v0.w);
-  o.z = pack_bf16(v1.x, v1.y);
-  o.w = pack_bf16(v1.z, v1.w);
-  *reinterpret_cast<uint4*>(cols + row * (3ll * P * P) + k) = o;
-}
-
-// Same gather, f32 output (tf32 mode keeps the patch matrix in fp32).
-__global__ void __launch_bounds__(256) im2col_f32_kernel(const float* __restrict__ px, float* __restrict__ cols, int B,
-                                                         int H, int W, int P, long long total, int row_stride, int row_off) {
-  ptx::grid_dep_launch();
-  ptx::grid_dep_wait();
-  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int w4 = W / 4;
-  const int x4 = static_cast<int>(t % w4);
-  long long r = t / w4;
-  const int y = static_cast<int>(r % H);
-  r /= H;
-  const int c = static_cast<int>(r % 3);
-  const int b = static_cast<int>(r / 3);
-  const float4 v = *reinterpret_cast<const float4*>(px + t * 4);
-  const int x = x4 * 4;
-  const int py = y / P, i = y % P, pxi = x / P, j = x % P;
-  const int gw = W / P;
-  const long long row = static_cast<long long>(b) * row_stride + row_off + py * gw + pxi;
-  const int k = (c * P + i) * P + j;
-  *reinterpret_cast<float4*>(cols + row * (3ll * P * P) + k) =
-      make_float4(ptx::round_tf32(v.x), ptx::round_tf32(v.y), ptx::round_tf32(v.z), ptx::round_tf32(v.w));
+  if (OUT_BF16) {
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cols_) + row * (3ll * P * P) + k) = o;
+  } else {  // tf32 mode keeps the patch matrix in fp32, rounded to nearest tf32 (the tensor core would truncate)
+    float* dst = reinterpret_cast<float*>(cols_) + row * (3ll * P * P) + k;
+    *reinterpret_cast<float4*>(dst) = make_float4(ptx::round_tf32(v[0]), ptx::round_tf32(v[1]), ptx::round_tf32(v[2]), ptx::round_tf32(v[3]));
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(ptx::round_tf32(v[4]), ptx::round_tf32(v[5]), ptx::round_tf32(v[6]), ptx::round_tf32(v[7]));
+  }
 }
 
 __global__ void __launch_bounds__(256) prefix_tokens_kernel(const float* __restrict__ prefix,
@@ -148,27 +164,46 @@ __global__ void __launch_bounds__(256) unfold_kernel(const TIN* __restrict__ x, 
 
 }  // namespace
 
-int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st, int row_stride,
-                  int row_off) {
+namespace {
+
+template <typename TIN, bool AFFINE>
+int im2col_typed(const void* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st, int row_stride,
+                 int row_off, const PixAffine& af) {
+  const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
+  const dim3 grid(static_cast<unsigned>((total + 255) / 256));
+  const bool pdl = pdl_for_rows(static_cast<long long>(B) * 256);
+  const TIN* px = reinterpret_cast<const TIN*>(pixels);
+  if (out_dtype == EVT_BF16)
+    EVT_CUDA(launch_pdl(im2col_kernel<TIN, true, AFFINE>, grid, dim3(256), 0, st, pdl, px, cols, B, H, W, P, total, row_stride, row_off, af));
+  else
+    EVT_CUDA(launch_pdl(im2col_kernel<TIN, false, AFFINE>, grid, dim3(256), 0, st, pdl, px, cols, B, H, W, P, total, row_stride, row_off, af));
+  EVT_LAUNCH_CHECK("im2col");
+  return EVT_OK;
+}
+
+}  // namespace
+
+int im2col_launch(const void* pixels, int pixel_dtype, const float* scale3, const float* bias3, void* cols, int out_dtype, int B,
+                  int H, int W, int P, cudaStream_t st, int row_stride, int row_off) {
   if (row_stride <= 0) row_stride = (H / (P > 0 ? P : 1)) * (W / (P > 0 ? P : 1)), row_off = 0;
   EVT_CHECK_ARG(pixels && cols, "im2col: null pointer");
   EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && P > 0, "im2col: sizes must be positive");
   EVT_CHECK_ARG(H % P == 0 && W % P == 0, "im2col: image size must be a multiple of the patch size");
-  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(pixels) % 16 == 0 && reinterpret_cast<uintptr_t>(cols) % 16 == 0,
-                "im2col: pointers must be 16-byte aligned");
-  if (P % 8 != 0 && P % 4 == 0 && out_dtype == EVT_BF16 && row_off == 0) return im2col4_launch(pixels, cols, B, H, W, P, st);  // Swin: P = 4
-  EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8 (bf16: of 4)");
-  if (out_dtype == EVT_BF16) {
-    const long long total = static_cast<long long>(B) * 3 * H * (W / 8);
-    EVT_CUDA(launch_pdl(im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
-                        reinterpret_cast<__nv_bfloat16*>(cols), B, H, W, P, total, row_stride, row_off));
-  } else {
-    const long long total = static_cast<long long>(B) * 3 * H * (W / 4);
-    EVT_CUDA(launch_pdl(im2col_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, pdl_for_rows(static_cast<long long>(B) * 256), pixels,
-                        reinterpret_cast<float*>(cols), B, H, W, P, total, row_stride, row_off));
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(cols) % 16 == 0, "im2col: output pointer must be 16-byte aligned");
+  const int in_bytes = pixel_dtype == EVT_PIX_F32 ? 4 : pixel_dtype == EVT_PIX_BF16 ? 2 : 1;
+  EVT_CHECK_ARG(pixel_dtype == EVT_PIX_F32 || pixel_dtype == EVT_PIX_BF16 || pixel_dtype == EVT_PIX_U8, "im2col: unknown pixel dtype");
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(pixels) % (8 * in_bytes) == 0, "im2col: pixel pointer must be aligned to 8 pixels");
+  if (P % 8 != 0 && P % 4 == 0 && out_dtype == EVT_BF16 && row_off == 0 && pixel_dtype == EVT_PIX_F32)
+    return im2col4_launch(reinterpret_cast<const float*>(pixels), cols, B, H, W, P, st);  // Swin: P = 4
+  EVT_CHECK_ARG(P % 8 == 0 && W % 8 == 0, "im2col: patch width must be a multiple of 8 (f32 pixels, bf16 output: of 4)");
+  PixAffine af = {{1.f, 1.f, 1.f}, {0.f, 0.f, 0.f}};
+  if (pixel_dtype == EVT_PIX_U8) {
+    EVT_CHECK_ARG(scale3 && bias3, "im2col: u8 pixels need a per-channel scale and bias");
+    for (int c = 0; c < 3; ++c) af.scale[c] = scale3[c], af.bias[c] = bias3[c];
+    return im2col_typed<uint8_t, true>(pixels, cols, out_dtype, B, H, W, P, st, row_stride, row_off, af);
   }
-  EVT_LAUNCH_CHECK("im2col");
-  return EVT_OK;
+  if (pixel_dtype == EVT_PIX_BF16) return im2col_typed<__nv_bfloat16, false>(pixels, cols, out_dtype, B, H, W, P, st, row_stride, row_off, af);
+  return im2col_typed<float, false>(pixels, cols, out_dtype, B, H, W, P, st, row_stride, row_off, af);
 }
 
 int embed_fill_launch(const float* prefix, const float* pos, const float* bias, float* out, int B, int tokens, int n_prefix, int D,
@@ -231,7 +266,7 @@ int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int
 extern "C" int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream) {
   int rc = evt_device_check();
   if (rc != EVT_OK) return rc;
-  return evt::im2col_launch(pixels, cols, EVT_BF16, B, H, W, P, static_cast<cudaStream_t>(stream));
+  return evt::im2col_launch(pixels, EVT_PIX_F32, nullptr, nullptr, cols, EVT_BF16, B, H, W, P, static_cast<cudaStream_t>(stream));
 }
 extern "C" int evt_prefix_tokens(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix,
                                  int D, evt_stream stream) {

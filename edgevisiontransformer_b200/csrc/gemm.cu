@@ -69,23 +69,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // the first pipeline stages are requested BEFORE the dependency wait, so their HBM round trip (weights are cold at batch
   // 1: each is read once per forward) overlaps the previous kernel's tail under programmatic dependent launch.
   int w_pre = 0;
-  if (p.w_static && warp == kProducerWarp && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) {
+  if (p.w_static && warp == kProducerWarp && static_cast<int>(blockIdx.x) < num_tiles) {
     const int item = blockIdx.x;
     const int tile = item / p.k_splits;
     const int kb0 = (item - tile * p.k_splits) * p.kb_per_split;
     const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
     const int n0 = (tile % p.tiles_n) * BN;
-    w_pre = min(C::kStages, kb1 - kb0);
-    for (int i = 0; i < w_pre; ++i) {
-      ptx::mbar_arrive_expect_tx(&full[i], C::kStageBytes);
-      ptx::tma_load_2d_hint(stage_base + i * C::kStageBytes + C::kABytes, &tmW, &full[i], (kb0 + i) * p.k_step, n0, ptx::kEvictLast);
+    w_pre = min(C::kStages, kb1 - kb0);  // warp-uniform; the elected thread of the producer loop below consumes it
+    if (ptx::elect_one()) {
+      for (int i = 0; i < w_pre; ++i) {
+        ptx::mbar_arrive_expect_tx(&full[i], C::kStageBytes);
+        ptx::tma_load_2d_hint(stage_base + i * C::kStageBytes + C::kABytes, &tmW, &full[i], (kb0 + i) * p.k_step, n0, ptx::kEvictLast);
+      }
     }
   }
   ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // One thread, chosen with elect.sync rather than `lane == 0`: ptxas then knows the region is single-threaded and keeps
+    // descriptors / coordinates in uniform registers.  Under a `lane == 0` guard every UTMALDG / UTCHMMA was wrapped in an
+    // ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop (~16 instructions per MMA, ncu round 2).
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
@@ -118,8 +123,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (one elected thread, see above)
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc(BM, BN, TF32 ? 2 : 1, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -182,7 +187,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         aphase ^= 1;
       }
     }
-    if (TMA_OUT && lane == 0) ptx::bulk_wait<0>();
+    if (TMA_OUT && ptx::elect_one()) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();

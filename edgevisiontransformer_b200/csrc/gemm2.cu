@@ -97,19 +97,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // Model-owned weights do not depend on the previous kernel: request the W half-tiles of the first pipeline stages before
   // the dependency wait (see gemm.cu; matters when programmatic dependent launch is on, i.e. for launches under ~100 us).
   int w_pre = 0;
-  if (p.w_static && warp == kProducerWarp && lane == 0 && pair < num_tiles) {
+  if (p.w_static && warp == kProducerWarp && pair < num_tiles) {
     const int n0 = (pair % p.tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
-    w_pre = min(C::kStages, p.num_kb);
-    for (int i = 0; i < w_pre; ++i) {
-      if (rank == 0) ptx::mbar_arrive_expect_tx(&full[i], 2 * C::kStageBytes);
-      ptx::tma_load_2d_pair(stage_base + i * C::kStageBytes + C::kABytes, &tmW, ptx::mapa(&full[i], 0), i * p.k_step, n0, ptx::kEvictLast);
+    w_pre = min(C::kStages, p.num_kb);  // warp-uniform; consumed by the elected producer thread below
+    if (ptx::elect_one()) {
+      for (int i = 0; i < w_pre; ++i) {
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&full[i], 2 * C::kStageBytes);
+        ptx::tma_load_2d_pair(stage_base + i * C::kStageBytes + C::kABytes, &tmW, ptx::mapa(&full[i], 0), i * p.k_step, n0, ptx::kEvictLast);
+      }
     }
   }
   ptx::grid_dep_wait();    // operands / outputs of the previous kernel are complete from here on
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // elect.sync, not `lane == 0`: ptxas keeps the single-threaded region on the uniform datapath (see gemm.cu)
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -139,7 +142,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc(2 * BM, BN, 1, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -206,7 +209,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         aphase ^= 1;
       }
     }
-    if (lane == 0) ptx::bulk_wait<0>();
+    if (ptx::elect_one()) ptx::bulk_wait<0>();
   }
 
   // Neither CTA may leave while the other can still reach into its shared memory / TMEM or signal its barriers.

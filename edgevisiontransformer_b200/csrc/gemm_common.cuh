@@ -297,9 +297,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         if constexpr (STG == 2) {
           stg = stg0 + (*stg_sel & 1) * kStgBytes;
           ++*stg_sel;
-          if (lane == 0) ptx::bulk_wait_read<1>();  // the store before the previous one has finished reading this tile
+          if (ptx::elect_one()) ptx::bulk_wait_read<1>();  // the store before the previous one has finished reading this tile
         } else {
-          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store of this warp has finished reading stg
+          if (ptx::elect_one()) ptx::bulk_wait_read<0>();  // the previous store of this warp has finished reading stg
         }
       }
       __syncwarp();
@@ -324,7 +324,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         // the residual stream at L2 -- the SM never reads the residual.
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (ptx::elect_one()) {  // the same thread every time (elect.sync is deterministic for a full mask): bulk groups are per thread
           if (has_res) ptx::tma_reduce_add_2d(tmO, stg, n0, m0);
           else ptx::tma_store_2d(tmO, stg, n0, m0);
           ptx::bulk_commit();

@@ -357,13 +357,16 @@ extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   return (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
-static int forward_impl(evt_model* m, const float* pixels, const void* patch_matrix, int64_t patch_ld, int batch,
-                        float* logits, void* workspace, size_t workspace_bytes, evt_stream stream) {
+static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts* opts, const void* patch_matrix, int64_t patch_ld,
+                        int batch, float* logits, void* workspace, size_t workspace_bytes, evt_stream stream) {
   EVT_CHECK_ARG(m != nullptr, "evt_model_forward: model is null");
   if (!m->loaded) return fail(EVT_ERR_STATE, "evt_model_forward called before evt_model_load_weights");
   EVT_CHECK_ARG((pixels || patch_matrix) && logits && workspace, "evt_model_forward: null pointer");
   EVT_CHECK_ARG(batch > 0 && batch <= 65535, "batch must be in 1..65535");
   const evt_model_spec& s = m->spec;
+  static const evt_forward_opts kNoOpts = {};
+  const evt_forward_opts& o = opts != nullptr ? *opts : kNoOpts;
+  EVT_CHECK_ARG(o.head_mask == nullptr || o.head_mask_ld > 0, "head_mask_ld must be positive when a head mask is given");
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   const size_t slack = reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(workspace);
   Workspace w = plan_workspace(m, batch, base);
@@ -412,7 +415,8 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
     EVT_CHECK_ARG(s.embed_k == 0, "this model takes a caller-built patch matrix (evt_model_forward_embedded)");
     const size_t row_bytes = static_cast<size_t>(m->patch_k) * m->es;
     EVT_CUDA(cudaMemset2DAsync(w.big, s.tokens * row_bytes, 0, m->n_prefix * row_bytes, batch, st));
-    EVT_STAGE(EVT_STAGE_EMBED, im2col_launch(pixels, w.big, dt, batch, s.image, s.image, s.patch, st, s.tokens, m->n_prefix));
+    EVT_STAGE(EVT_STAGE_EMBED, im2col_launch(pixels, o.pixel_dtype, o.pixel_scale, o.pixel_bias, w.big, dt, batch, s.image, s.image, s.patch, st,
+                                             s.tokens, m->n_prefix));
     EVT_STAGE(EVT_STAGE_EMBED, embed_fill_launch(m->prefix, m->pos, m->b_patch, w.resid, batch, s.tokens, m->n_prefix, D, st));
     EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.big, m->patch_k, m->w_patch, m->patch_k, dt, nullptr, w.resid, D, 0, 0, w.resid, EVT_F32, D,
                                            0, 0, 0, M, D, m->patch_k, EVT_ACT_NONE, st));
@@ -427,8 +431,12 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
   // FOLLOWS each residual projection can run inside that GEMM's epilogue (gemm3.cu).  It is bit-identical on the residual
   // stream but measured SLOWER on B200 (0.42 vs 0.22 ms for out-proj + LN at 100k rows): the second pass over the new
   // residual does not stay in L2 (DRAM reads 750 MB vs 465 MB expected), so no traffic is saved -- see DESIGN.md.
+#ifdef EVT_EXPERIMENTAL
   const bool fuse_ln = !tf32 && !tf && gemm_ln_fusion_enabled() && gemm_res_ln_supported(M, D, D) &&
                        (M + 255) / 256 >= num_sms() / 2;
+#else
+  constexpr bool fuse_ln = false;  // gemm3.cu is only built with EVT_EXPERIMENTAL=1 (edgevisiontransformer_b200/build.py)
+#endif
   bool xn_ready = false;  // w.xn already holds LN1 of the current layer (written by the previous layer's FC2 epilogue)
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
@@ -438,26 +446,38 @@ static int forward_impl(evt_model* m, const float* pixels, const void* patch_mat
     xn_ready = false;
     EVT_STAGE(EVT_STAGE_QKV, gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
                         EVT_ACT_NONE, st));
+    // head mask row of this layer (are_16_heads mask_heads) and, on request, the context written straight into the caller's
+    // buffer (context_layer_val): the output projection then reads its A operand from there
+    const float* hmask = o.head_mask != nullptr ? o.head_mask + static_cast<size_t>(l) * o.head_mask_ld : nullptr;
+    EVT_CHECK_ARG(hmask == nullptr || o.head_mask_ld >= s.heads[l], "head_mask_ld smaller than a layer's head count");
+    uint8_t* ctx = (o.ctx_out != nullptr && o.ctx_out[l] != nullptr) ? reinterpret_cast<uint8_t*>(o.ctx_out[l]) : w.ctx;
+    EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(ctx) % 16 == 0, "ctx_out pointers must be 16-byte aligned");
     if (tf32)
-      EVT_STAGE(EVT_STAGE_ATTN, attention_tf32_launch(reinterpret_cast<const float*>(w.qkv), 3 * a, reinterpret_cast<float*>(w.ctx), a, nullptr,
+      EVT_STAGE(EVT_STAGE_ATTN, attention_tf32_launch(reinterpret_cast<const float*>(w.qkv), 3 * a, reinterpret_cast<float*>(ctx), a, hmask,
                                     batch, s.tokens, s.heads[l], s.head_size, scale, st));
     else
-      EVT_STAGE(EVT_STAGE_ATTN, attention_launch(w.qkv, 3 * a, w.ctx, a, nullptr, batch, s.tokens, s.heads[l], s.head_size, scale, st));
+      EVT_STAGE(EVT_STAGE_ATTN, attention_launch(w.qkv, 3 * a, ctx, a, hmask, batch, s.tokens, s.heads[l], s.head_size, scale, st));
+#ifdef EVT_EXPERIMENTAL
     if (fuse_ln) {
-      EVT_STAGE(EVT_STAGE_OPROJ, gemm_res_ln_launch(w.ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
-    } else {
-      EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(w.ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
+      EVT_STAGE(EVT_STAGE_OPROJ, gemm_res_ln_launch(ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
+    } else
+#endif
+    {
+      EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
                           EVT_ACT_NONE, st));
       EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
     }
     EVT_STAGE(EVT_STAGE_FC1, gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
                         st));
+#ifdef EVT_EXPERIMENTAL
     if (fuse_ln && l + 1 < s.layers) {
       const LayerW& nx = m->layers[l + 1];
       EVT_STAGE(EVT_STAGE_FC2, gemm_res_ln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, w.xn, D,
                                  M, D, lw.inter, st));
       xn_ready = true;
-    } else {
+    } else
+#endif
+    {
       EVT_STAGE(EVT_STAGE_FC2, gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M,
                           D, lw.inter, EVT_ACT_NONE, st));
     }
@@ -522,11 +542,34 @@ extern "C" int evt_model_profile_end(evt_model* m, float* stage_ms, int* stage_l
 extern "C" int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits, void* workspace,
                                  size_t workspace_bytes, evt_stream stream) {
   EVT_CHECK_ARG(pixels != nullptr, "evt_model_forward: pixels is null");
-  return forward_impl(m, pixels, nullptr, 0, batch, logits, workspace, workspace_bytes, stream);
+  return forward_impl(m, pixels, nullptr, nullptr, 0, batch, logits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int evt_model_forward_ex(evt_model* m, const void* pixels, const evt_forward_opts* opts, int batch, float* logits,
+                                    void* workspace, size_t workspace_bytes, evt_stream stream) {
+  EVT_CHECK_ARG(pixels != nullptr, "evt_model_forward_ex: pixels is null");
+  return forward_impl(m, pixels, opts, nullptr, 0, batch, logits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int evt_model_forward_embedded(evt_model* m, const void* patch_matrix, int64_t ld, int batch, float* logits,
                                           void* workspace, size_t workspace_bytes, evt_stream stream) {
   EVT_CHECK_ARG(patch_matrix != nullptr, "evt_model_forward_embedded: patch_matrix is null");
-  return forward_impl(m, nullptr, patch_matrix, ld, batch, logits, workspace, workspace_bytes, stream);
+  return forward_impl(m, nullptr, nullptr, patch_matrix, ld, batch, logits, workspace, workspace_bytes, stream);
 }
+
+#ifndef EVT_EXPERIMENTAL
+// The single-kernel version (gemm3.cu) measured slower than the two kernels it replaces (negative results) and is
+// only built with EVT_EXPERIMENTAL=1; the entry point keeps its contract by issuing those two kernels.
+extern "C" int evt_gemm_residual_layernorm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid,
+                                           int64_t ldr, const float* gamma, const float* beta, float eps, void* xn, int64_t ldxn,
+                                           int64_t M, int N, int K, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  EVT_CHECK_ARG(resid != nullptr && xn != nullptr && gamma != nullptr && beta != nullptr, "gemm_residual_layernorm: null pointer");
+  if (N % 64 != 0 || N < 64 || N > 1024) return fail(EVT_ERR_UNSUPPORTED, "gemm+ln: N must be a multiple of 64 in [64, 1024]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = gemm_launch(A, lda, W, ldw, EVT_BF16, bias, resid, ldr, 0, 0, resid, EVT_F32, ldr, 0, 0, 0, M, N, K, EVT_ACT_NONE, st);
+  if (rc != EVT_OK) return rc;
+  return layernorm_launch(resid, ldr, gamma, beta, xn, EVT_BF16, ldxn, nullptr, M, N, eps, st);
+}
+#endif

@@ -25,8 +25,9 @@ int layernorm_launch(const float* x, int64_t x_stride, const float* gamma, const
                      int64_t y_stride, float* y_copy, int64_t rows, int D, float eps, cudaStream_t st);
 
 // row_stride > 0: patch p of image b is written to row b * row_stride + row_off + p (one row per token); 0 = dense patch matrix
-int im2col_launch(const float* pixels, void* cols, int out_dtype, int B, int H, int W, int P, cudaStream_t st, int row_stride = 0,
-                  int row_off = 0);
+// pixel_dtype: evt_pixel_dtype; scale3 / bias3 (host, 3 floats each): per-channel affine applied to u8 pixels
+int im2col_launch(const void* pixels, int pixel_dtype, const float* scale3, const float* bias3, void* cols, int out_dtype, int B,
+                  int H, int W, int P, cudaStream_t st, int row_stride = 0, int row_off = 0);
 int embed_fill_launch(const float* prefix, const float* pos, const float* bias, float* out, int B, int tokens, int n_prefix, int D,
                       cudaStream_t st);
 int im2col4_launch(const float* pixels, void* cols, int B, int H, int W, int P, cudaStream_t st);  // swin.cu, P % 4 == 0

@@ -255,6 +255,27 @@ int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* out);
 /* logits[batch, num_labels] (f32) = forward(pixels f32 NCHW [batch,3,image,image]); async on stream. */
 int evt_model_forward(evt_model* m, const float* pixels, int batch, float* logits,
                       void* workspace, size_t workspace_bytes, evt_stream stream);
+/* Pixel storage accepted by evt_model_forward_ex: the conversion is fused into the patch gather (im2col), so a caller that
+ * keeps bf16 or raw u8 images in pinned host memory moves 2x / 4x fewer bytes over PCIe than with f32. */
+enum evt_pixel_dtype { EVT_PIX_F32 = 0, EVT_PIX_BF16 = 1, EVT_PIX_U8 = 2 };
+
+/* Optional inputs / outputs of one forward.  A zero-initialised struct == evt_model_forward. */
+typedef struct evt_forward_opts {
+  int pixel_dtype;           /* evt_pixel_dtype of `pixels` (NCHW [batch,3,image,image])                                    */
+  float pixel_scale[3];      /* EVT_PIX_U8 only: value = pixel * scale[c] + bias[c], i.e. scale = 1/(255 std[c]),           */
+  float pixel_bias[3];       /*   bias = -mean[c]/std[c] -- torchvision Normalize, deit_pruning/src/utils.py:118-133        */
+  const float* head_mask;    /* NULL, or DEVICE f32 [layers, head_mask_ld]: head h of layer l is multiplied by              */
+  int head_mask_ld;          /*   head_mask[l*ld + h] (h < heads[l]) -- HF forward(head_mask=...) and are_16_heads           */
+                             /*   `model.vit.mask_heads(to_prune)`, are_16_heads/run_classifier.py:247-250                   */
+  void* const* ctx_out;      /* NULL, or HOST array of `layers` DEVICE pointers (entries may be NULL): layer l's attention   */
+                             /*   context before the output projection, [batch*tokens, heads[l]*64] in the operand type      */
+                             /*   (bf16; f32 in tf32 mode) = `context_layer_val` of are_16_heads/classifier_eval.py:183-191  */
+                             /*   (reshape to [batch, tokens, heads, 64] and permute to [batch, heads, tokens, 64])          */
+} evt_forward_opts;
+
+/* evt_model_forward with options (opts may be NULL).  Same launch count, same workspace. */
+int evt_model_forward_ex(evt_model* m, const void* pixels, const evt_forward_opts* opts, int batch, float* logits,
+                         void* workspace, size_t workspace_bytes, evt_stream stream);
 /* Same forward, starting from the A operand of the token-embedding GEMM instead of pixels: patch_matrix is
  * [batch*patches, ld] in the operand type of the model's precision (bf16, or f32 for tf32).  Used by the T2T front-end
  * (tokens-to-token module, modeling/models/t2t_vit.py:63-88), whose last soft split produces exactly that matrix. */
