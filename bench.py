@@ -41,6 +41,53 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
+def matmul_gflop(hidden, heads, inter, tokens=197, labels=1000, patches=196, patch_k=768):
+    """algorithmic matmul FLOPs per image, 2 M N K per GEMM, HF dialect."""
+    f = 2.0 * patches * patch_k * hidden
+    for h, i in zip(heads, inter):
+        a = 64 * h
+        f += 3 * 2 * tokens * hidden * a + 2 * 2 * tokens * tokens * a + 2 * tokens * a * hidden + 2 * 2 * tokens * hidden * i
+    return (f + 2.0 * hidden * labels) / 1e9
+
+
+def hbm_mb_per_img(hidden, heads, inter, tokens=197):
+    """algorithmic HBM bytes per image (bf16 activations, one pass per op with epilogue fusion,
+    LayerNorm separate, weights amortised): per layer 2 S [2D + (D+3a) + (3a+a) + (a+2D) + 2D + (D+i) + (i+2D)]."""
+    b = 0.0
+    for h, i in zip(heads, inter):
+        a, D = 64 * h, hidden
+        b += 2.0 * tokens * (2 * D + (D + 3 * a) + (3 * a + a) + (a + 2 * D) + 2 * D + (D + i) + (i + 2 * D))
+    return b / 1e6
+
+
+def traffic_lookup(kernel: str, M: int, N: int, K: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel at a shape, from the committed ncu
+    captures indexed in profiles/traffic.json.  No matching capture -> (None, True): the line then says traffic_stale."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        tab = json.load(open(p))
+    except Exception:
+        return None, True, None
+    ent = tab.get(f"{kernel}|M={M},N={N},K={K}")
+    if not ent:
+        return None, True, None
+    return float(ent["dram_read"]) + float(ent["dram_write"]), False, ent.get("source")
+
+
+def timed_steps(fn, steps, warmup=3):
+    """CUDA-event time per call on the current stream after `warmup` untimed calls."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def build_hf(workload: str, seed: int = 0):
     """Random-init HF ViTForImageClassification of the named architecture (no checkpoints offline)."""
     from transformers import ViTConfig, ViTForImageClassification
@@ -147,6 +194,125 @@ def run_reference(args):
     return 0
 
 
+def pruned_tiny_state_dict(case: str):
+    """BASELINE config 4 on random-init DeiT-Tiny weights, built the way the reference's eval does it (eval_main.py:87-103):
+    nn_pruning leaves all-zero FC1 rows / FC2 columns and zeroed head blocks in a full-size checkpoint; the product's
+    checkpoint surgery (prune_heads_ / drop_zero_ffn_ = HF prune_heads + optimize_model) then yields the small shapes.
+      h1_d230        layerwise_thresholds "h_0.50_d_0.3" x 12: 1 head, 230 FFN units per layer
+      head18_uneven  are16heads tiny-18 heads [1,1,1,1,2,1,2,2,2,2,1,2] (draw.py:104-106) with uneven FFN widths"""
+    from edgevisiontransformer_b200 import checkpoint as ck
+    from edgevisiontransformer_b200.modeling_vit import normalise_keys
+    sd = normalise_keys({k: v.detach().clone() for k, v in build_hf("deit_tiny").state_dict().items()})
+    if case == "h1_d230":
+        heads, inter = [1] * 12, [230] * 12
+    else:
+        heads, inter = [1, 1, 1, 1, 2, 1, 2, 2, 2, 2, 1, 2], [230, 231, 200, 256, 1, 8, 407, 230, 300, 150, 768, 64]
+    g = torch.Generator().manual_seed(7)
+    for l in range(12):
+        p = f"vit.encoder.layer.{l}."
+        drop = torch.randperm(768, generator=g)[: 768 - inter[l]]
+        sd[p + "intermediate.dense.weight"][drop] = 0
+        sd[p + "intermediate.dense.bias"][drop] = 0
+        sd[p + "output.dense.weight"][:, drop] = 0
+    ck.prune_heads_(sd, {l: list(range(heads[l], 3)) for l in range(12)}, 64, n_orig=3)
+    ck.drop_zero_ffn_(sd)
+    return sd, heads, inter
+
+
+def extra_configs(dev, steps, pk):
+    """BASELINE configs 2, 4 and 5 in the same run (device-resident inputs, CUDA events): images/s and the roofline
+    fraction SURVEY.md section 8d assigns to each (tensor for Small and T2T, HBM for the pruned Tiny)."""
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    from edgevisiontransformer_b200.benchmark.b200 import _random_t2t_weights
+    out = {}
+
+    def run(name, model, x, batch, gflop, hbm_mb=None, note=None):
+        ms = timed_steps(lambda: model(x).logits, steps, warmup=3)
+        ips = batch / ms * 1e3
+        ent = {"batch": batch, "img_per_s": ips, "ms_per_forward": ms, "gflop_per_img": gflop, "model_tflops": ips * gflop / 1e3,
+               "frac_tensor_sustained": ips * gflop / 1e3 / pk["tf_sustained"], "steps": steps}
+        if hbm_mb is not None:
+            ent["hbm_mb_per_img"] = hbm_mb
+            ent["hbm_roofline_img_per_s"] = pk["hbm_gbs"] * 1e3 / hbm_mb
+            ent["frac_hbm"] = ips / ent["hbm_roofline_img_per_s"]
+        if note:
+            ent["note"] = note
+        out[name] = ent
+
+    m = B200ViTForImageClassification.from_hf(build_hf("deit_small"), device=dev, max_batch=256, keep_params=False)
+    x = torch.randn(256, 3, 224, 224, device=dev)
+    run("config2_deit_small_bs256", m, x, 256, GFLOP_PER_IMG["deit_small"], hbm_mb_per_img(384, [6] * 12, [1536] * 12))
+    del m
+    x = torch.randn(1024, 3, 224, 224, device=dev)
+    for case in ("h1_d230", "head18_uneven"):
+        sd, heads, inter = pruned_tiny_state_dict(case)
+        m = B200ViTForImageClassification.from_state_dict(sd, device=dev, max_batch=1024, keep_params=False)
+        assert m.config.heads == heads and m.config.intermediate == inter
+        run(f"config4_pruned_tiny_{case}_bs1024", m, x, 1024, matmul_gflop(192, heads, inter), hbm_mb_per_img(192, heads, inter),
+            note="HBM-bound config: frac_hbm is the roofline fraction")
+        del m
+    from edgevisiontransformer_b200.modeling_t2t import B200T2TViT
+    m = B200T2TViT(_random_t2t_weights(384, 14, 6, 3.0), depth=14, num_heads=6, device=dev, max_batch=256)
+    x = torch.randn(1024, 224, 224, 3, device=dev)
+    run("config5_t2t_vit_14_bs1024", m, x, 1024, 9.567, note="NHWC input, chunks of 256; 9.567 GF/img = front-end 0.598 + encoder 8.969")
+    del m, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def library_baseline(dev, batch, steps):
+    """the reference's own module (HF ViTForImageClassification, DeiT-Base) in bf16 on the SAME GPU
+    through stock PyTorch kernels (cuBLAS + SDPA, and eager attention as the reference's pinned transformers runs it)."""
+    from transformers import ViTConfig, ViTForImageClassification
+    out = {"what": "HF ViTForImageClassification DeiT-Base bf16 on this GPU via stock PyTorch (cuBLAS/cuDNN/ATen)", "batch": batch,
+           "torch": torch.__version__}
+    x = torch.randn(batch, 3, 224, 224, device=dev, dtype=torch.bfloat16)
+    for impl in ("sdpa", "eager"):
+        cfg = ViTConfig(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, num_labels=1000,
+                        image_size=224, patch_size=16, attn_implementation=impl)
+        torch.manual_seed(0)
+        model = ViTForImageClassification(cfg).eval().to(dev).bfloat16()
+        with torch.no_grad():
+            ms = timed_steps(lambda: model(pixel_values=x).logits, steps, warmup=3)
+        out[impl + "_img_per_s"] = batch / ms * 1e3
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def config1_latency(dev, runs=200):
+    """BASELINE config 1 as written: DeiT-Tiny patch16-224, random-init (seed 0), batch 1, the tf32 accuracy mode: p50
+    over `runs` CUDA-graph replays, and max-abs error / top-1 agreement against the reference's fp32 forward on the CPU
+    (the HF module itself, not the oracle) on the same synthetic image."""
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    hf = build_hf("deit_tiny", seed=0)
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    out = {}
+    for prec in ("tf32", "bf16"):
+        m = B200ViTForImageClassification.from_hf(hf, device=dev, max_batch=1, precision=prec, keep_params=False)
+        xd = x.to(dev)
+        for _ in range(30):
+            got = m.forward_graphed(xd).logits
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(runs):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.forward_graphed(xd)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        out[prec] = {"p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "runs": runs,
+                     "max_abs_vs_reference_fp32": float((got.cpu() - want).abs().max()),
+                     "top1_agrees": bool((got.cpu().argmax(-1) == want.argmax(-1)).all())}
+        del m
+    out["model"] = "deit_tiny patch16-224 random-init seed 0, batch 1, synthetic randn image seed 1"
+    out["tolerance"] = {"tf32": 1e-3, "bf16": 2e-2}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,7 +323,9 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=1024, help="images per forward call inside a step")
     ap.add_argument("--ref-batch", type=int, default=16)
+    ap.add_argument("--preroll-s", type=float, default=2.0, help="seconds of untimed steps before the timed region (sustained clocks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs, the library baseline and config 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,14 +359,24 @@ def main():
     def step():
         return model(x).logits
 
-    for _ in range(max(args.warmup, 3)):
-        out = step()
-    torch.cuda.synchronize()
-
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = step()
+    torch.cuda.synchronize()
+    # Power pre-roll: the same step, untimed, for >= preroll_s on every rank, so that the timed steps run at the clocks
+    # the GPU SUSTAINS under its power cap.  Without it a short timed region (8 GPUs: 0.4 s) runs at boost clocks and the
+    # scaling efficiency reads above 1 (round-1 verdict).
+    pre_steps = 0
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.preroll_s:
+        step()
+        torch.cuda.synchronize()
+        pre_steps += 1
 
     # ------------------------------------------------------------------ timed region (device-resident inputs)
     barrier()
@@ -221,25 +399,41 @@ def main():
     assert torch.isfinite(out).all()
 
     # ------------------------------------------------------------------ end to end through the public API, host buffers
+    # Headline e2e: f32 pinned pixels (what the reference's loader hands over).  The C ABI also takes bf16 and raw u8
+    # pixels (conversion / normalisation fused into the patch gather): 2x / 4x fewer bytes over PCIe, reported beside it.
     from edgevisiontransformer_b200.eval_loop import PipelinedClassifier
     runner = PipelinedClassifier(model, chunk=chunk)
+
+    def e2e_run(host):
+        for _ in range(2):
+            runner.logits(host)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            lg = runner.logits(host)             # H2D (pinned, chunked, overlapped) -> forward -> D2H logits
+        e1.record()
+        torch.cuda.synchronize()
+        el = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        tt = torch.tensor([el], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        assert lg.shape == (per, 1000) and not lg.is_cuda
+        return gbatch / (float(tt.item()) / args.steps / 1e3)
+
     host = torch.empty((per, 3, 224, 224), dtype=torch.float32).pin_memory()
     host.copy_(x)
-    for _ in range(2):
-        runner.logits(host)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        lg = runner.logits(host)                 # H2D (pinned, chunked, overlapped) -> forward -> D2H logits
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = gbatch / (float(t.item()) / args.steps / 1e3)
-    assert lg.shape == (per, 1000) and not lg.is_cuda
+    e2e_value = e2e_run(host)
+    e2e_alt = {}
+    hb = torch.empty((per, 3, 224, 224), dtype=torch.bfloat16).pin_memory()
+    hb.copy_(x)
+    del host
+    e2e_alt["bf16_pixels"] = {"value": e2e_run(hb), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 2}
+    del hb
+    hu = torch.randint(0, 256, (per, 3, 224, 224), dtype=torch.uint8).pin_memory()
+    e2e_alt["u8_pixels"] = {"value": e2e_run(hu), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224,
+                            "note": "raw uint8 images, ImageNet mean/std normalisation fused into the patch gather"}
+    del hu
 
     # ------------------------------------------------------------------ roofline of the dominant kernel (FC1 GEMM)
     # Second pass over the SAME K steps with the library's event tap on: a CUDA event on the launching stream after
@@ -270,26 +464,20 @@ def main():
         w = (torch.randn(inter, d, device=dev) * 0.02).bfloat16()
         b = torch.zeros(inter, device=dev)
         o = torch.empty(M, inter, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            ops.linear(a, w, b, act="gelu_erf", out=o)
-        reps = 10
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            ops.linear(a, w, b, act="gelu_erf", out=o)
-        e1.record()
-        torch.cuda.synchronize()
-        alone_ms = e0.elapsed_time(e1) / reps
+        alone_ms = timed_steps(lambda: ops.linear(a, w, b, act="gelu_erf", out=o), 10, warmup=3)
         alone = flops / (alone_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_pair_kernel<256,bf16,gelu_erf> (FC1: M=%d N=%d K=%d)" % (M, inter, d),
+        kname = "gemm_pair_kernel<256,bf16,gelu_erf>"
+        traffic, stale, tsrc = traffic_lookup(kname, M, inter, d)
+        roof = {"bound": "tensor", "kernel": "%s (FC1: M=%d N=%d K=%d)" % (kname, M, inter, d),
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "peak_source": pk["src"] + " (sustained: kernel timed inside the step, %d launches)" % fc1_n,
                 "ms_per_launch": kms, "share_of_step": fc1_ms / tot,
                 "alone": {"achieved": alone, "peak": pk["tf_burst"], "frac": alone / pk["tf_burst"], "ms_per_launch": alone_ms,
                           "peak_source": pk["src"] + " (burst: kernel timed alone)"},
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, from the committed
-                # ncu --set full capture profiles/r01_layer_ncu_full.md: 0.323 GB read + 1.187 GB written (algorithmic: A 0.310 + out 1.239 + W 0.005 GB)
-                "traffic": 1.510e9 if (M, inter, d) == (201728, 3072, 768) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, looked up in the index of
+                # committed ncu --set full captures (profiles/traffic.json); null + traffic_stale when no capture matches
+                "traffic": traffic, "traffic_stale": stale, "traffic_source": tsrc,
+                "algorithmic_bytes": 2.0 * M * d + 2.0 * inter * d + 2.0 * M * inter,
                 "model_frac_sustained": value / n_gpus * GFLOP_PER_IMG[args.workload] / 1e3 / pk["tf_sustained"]}
         del a, w, b, o
 
@@ -308,8 +496,16 @@ def main():
             torch.cuda.synchronize()
             ts.append((time.perf_counter() - t0) * 1e3)
         ts.sort()
-        lat = {"batch": 1, "p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "runs": len(ts),
+        lat = {"batch": 1, "model": args.workload + " bf16", "p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "runs": len(ts),
                "how": "CUDA-graph replay of the forward incl. the device-side input copy, host wall clock around each run"}
+
+    extras, lib_base = None, None
+    if rank == 0 and n_gpus == 1 and not args.no_extras:
+        del x
+        torch.cuda.empty_cache()
+        lat["config1"] = config1_latency(dev)
+        extras = extra_configs(dev, max(5, min(args.steps, 10)), pk)
+        lib_base = library_baseline(dev, chunk, 5)
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -321,18 +517,21 @@ def main():
     if rank == 0:
         line = {
             "metric": "images_per_sec", "value": value, "unit": "img/s", "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload} patch16-224 bf16 forward, random-init weights", "global_batch": gbatch,
                        "per_gpu_batch": per, "chunk": chunk, "parallelism": f"batch-sharded x{n_gpus}, no collective",
-                       "l2": "inputs larger than L2 (%.0f MB of pixels per step)" % (per * 3 * 224 * 224 * 4 / 1e6)},
+                       "l2": "inputs larger than L2 (%.0f MB of pixels per step)" % (per * 3 * 224 * 224 * 4 / 1e6),
+                       "preroll": "%d untimed steps over %.1f s before the timed region (sustained clocks)" % (pre_steps, args.preroll_s)},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 4,
-                    "d2h_bytes_per_step": per * 1000 * 4},
+                    "d2h_bytes_per_step": per * 1000 * 4, "pixels": "f32 pinned host memory", "other_pixel_types": e2e_alt},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
             "stages": stage_line,
             "latency": lat,
+            "configs": extras,
+            "gpu_library_baseline": lib_base,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

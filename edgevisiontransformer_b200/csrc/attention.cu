@@ -246,6 +246,7 @@ __device__ __forceinline__ float softmax_row(uint32_t t_row, int n16, int last_v
   return sum;
 }
 
+#ifdef EVT_EXPERIMENTAL  // the round-1 kernel, kept for A/B timing (EVT_ATTN_V1=1)
 __global__ void __launch_bounds__(kThreadsP, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -446,6 +447,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 
 
+#endif  // EVT_EXPERIMENTAL
+
 // ------------------------------------------------------------------------------------------------------------
 // Round-2 kernel.  Same arithmetic and TMEM slot layout as attention_kernel above (the softmax code is shared); what
 // changed is everything around it, driven by the round-1 warp-sample profile (56 % of the softmax warps' time was spent
@@ -459,6 +462,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //   * the context tile leaves through a 128B-swizzled staging tile and a 3-D TMA store (box = 32 rows of one image, rows
 //     past the sequence end clipped by the tensor map) instead of 32 scattered 16-byte stores per instruction, whose
 //     source registers held the warp for 13 % of its time.
+//   * a query tile is assembled from four 32-row TMA boxes, one per TMEM lane quadrant, and the assignment of an image's
+//     32-row blocks to quadrants ROTATES from unit to unit (quadrant q of tile t holds block 4t + ((q - r) & 3), r = unit
+//     & 3).  S = 197 is 6 full blocks + one 5-row block + one empty slot: unrotated, the softmax warps of quadrants 0 and 1
+//     (= SM sub-partitions 0 and 1) always had two full blocks per (image, head) while quadrant 3 had one; rotated, every
+//     sub-partition gets 7 blocks per 4 units.
 constexpr int kQKWarp = 9;
 constexpr int kPVWarp = 10;
 constexpr int kThreads2 = 32 * (kSoftmaxWarps + 3);
@@ -472,6 +480,7 @@ struct Attn2Params {
   int n_mt;      // query tiles per work unit (q_tiles, or 1 when the tiles of a pair are split across CTAs)
   int q_tiles;   // query tiles per (image, head)
   int n_kv;      // K/V ring depth
+  int rot_mask;  // 3: rotate the block -> quadrant assignment from unit to unit; 0: fixed (EVT_ATTN_NOROT=1, A/B timing)
   float scale_log2e;
 };
 
@@ -493,6 +502,8 @@ __device__ __forceinline__ Unit unit_of(const Attn2Params& p, int ql) {
 }
 // query tile of item s (0 .. n_mt-1) of unit ql: the order flips on every other unit so that both softmax groups see
 // full and ragged tiles
+// 32-row block of the image held by TMEM lane quadrant `quad` of query tile `mt` in unit ql (see the header comment)
+__device__ __forceinline__ int block_of(int mt, int quad, int rot) { return 4 * mt + ((quad - rot) & 3); }
 __device__ __forceinline__ int tile_of(const Attn2Params& p, const Unit& u, int ql, int s) {
   if (p.n_mt != p.q_tiles) return u.mt0;
   return p.n_mt == 2 ? (s ^ (ql & 1)) : s;
@@ -569,7 +580,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const int g = j & 1;
           ptx::mbar_wait(&q_empty[g], ((j >> 1) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&q_full[g], kQTileBytes);
-          ptx::tma_load_2d(q_ring + g * kQTileBytes, &tmQ, &q_full[g], u.h * kHD, row0 + tile_of(p, u, ql, s) * kQRows);
+          const int mt = tile_of(p, u, ql, s);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)  // rows past the end of the image (and whole empty blocks) arrive as zeros
+            ptx::tma_load_3d(q_ring + g * kQTileBytes + q * kStgWarpBytes, &tmQ, &q_full[g], u.h * kHD, 32 * block_of(mt, q, ql & p.rot_mask), u.b);
         }
         if (++kst == p.n_kv) {
           kst = 0;
@@ -668,8 +682,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
       const int mt = tile_of(p, u, ql, p.n_mt == 2 ? grp : 0);
-      const int qrow0 = mt * kQRows + quad * 32;
-      const bool warp_live = qrow0 < p.S;  // rows 224..255 of the second tile when S = 197: nothing to do
+      const int qrow0 = 32 * block_of(mt, quad, ql & p.rot_mask);
+      const bool warp_live = qrow0 < p.S;  // block 7 (rows 224..255) when S = 197: nothing to do
       float hm = 1.f;
       if (p.head_mask != nullptr) hm = p.head_mask[u.h];
       ptx::mbar_wait(&s_ready[grp], ph);
@@ -1063,7 +1077,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   ptx::grid_dep_wait();  // qkv (previous kernel's output) is complete from here on
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const int row0 = b * p.S;
       ptx::mbar_arrive_expect_tx(bar_load, 2 * kQRows * 128 + 2 * k_atom);
       for (int t = 0; t < 2; ++t) {
@@ -1193,92 +1207,97 @@ int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const
   EVT_CHECK_ARG(ldc % 8 == 0 && reinterpret_cast<uintptr_t>(ctx) % 16 == 0, "attention: ctx must be 16-byte aligned rows");
   EVT_CHECK_ARG(static_cast<int64_t>(B) * S < (1ll << 31) - 512, "attention: B*S too large");
   const int SK = (S + 15) / 16 * 16;
-  CUtensorMap tmQ, tmKV;
   const uint64_t rows = static_cast<uint64_t>(B) * S;
-  int rc = make_tmap_2d(&tmQ, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), kQRows, kHD);
-  if (rc != EVT_OK) return rc;
-  rc = make_tmap_2d(&tmKV, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), SK, kHD);
-  if (rc != EVT_OK) return rc;
-  AttnParams p;
-  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
-  p.head_mask = head_mask;
-  p.ldc = ldc;
-  p.S = S;
-  p.SK = SK;
-  p.heads = heads;
-  p.B = B;
-  p.q_tiles = (S + kQRows - 1) / kQRows;
+  const int q_tiles = (S + kQRows - 1) / kQRows;
   const long long n_pairs = static_cast<long long>(B) * heads;
-  p.n_mt = (p.q_tiles > 1 && n_pairs * p.q_tiles <= num_sms()) ? 1 : p.q_tiles;  // split the tiles across CTAs at small batch
-  p.scale_log2e = scale * 1.4426950408889634f;
-  const int stage_bytes = kQRows * 128 + 2 * SK * 128;
-  const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
+  const int n_mt = (q_tiles > 1 && n_pairs * q_tiles <= num_sms()) ? 1 : q_tiles;  // split the tiles across CTAs at small batch
+  const float scale_log2e = scale * 1.4426950408889634f;
   const int max_smem = 232448;
-  int n_stages = (max_smem - 1024 - bar_bytes) / stage_bytes;
-  if (n_stages > kMaxStages) n_stages = kMaxStages;
-  if (n_stages < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two shared-memory stages");
-  p.n_stages = n_stages;
-  const int smem = 1024 + n_stages * stage_bytes + bar_bytes;
-  static int configured_dev = -1;
+  const long long units = n_pairs * (q_tiles / n_mt);
+  const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
+  const bool pdl = pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD);
   int dev = 0;
   EVT_CUDA(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured_dev = dev;
-  }
-  const long long units = n_pairs * (p.q_tiles / p.n_mt);
-  const int grid = units < num_sms() ? static_cast<int>(units) : num_sms();
-  static const bool use_v1 = getenv("EVT_ATTN_V1") != nullptr && atoi(getenv("EVT_ATTN_V1")) != 0;  // round-1 kernel, for A/B timing
-  if (!use_v1) {
-    CUtensorMap tmO;
-    rc = make_tmap_3d_rows(&tmO, ctx, 2, static_cast<uint64_t>(heads) * kHD, static_cast<uint64_t>(S), static_cast<uint64_t>(B),
-                           static_cast<uint64_t>(ldc), 32, kHD);
-    if (rc != EVT_OK) return rc;
-    Attn2Params q;
-    q.head_mask = head_mask;
-    q.S = S;
-    q.SK = SK;
-    q.heads = heads;
-    q.B = B;
-    q.n_mt = p.n_mt;
-    q.q_tiles = p.q_tiles;
-    q.scale_log2e = p.scale_log2e;
-    const int fixed = 1024 + 2 * kQTileBytes + kSoftmaxWarps * kStgWarpBytes + (2 * kMaxKV + 12) * 8 + 16;
-    int n_kv = (max_smem - fixed) / (2 * SK * 128);
-    if (n_kv > kMaxKV) n_kv = kMaxKV;
-    if (n_kv < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two K/V stages");
-    q.n_kv = n_kv;
-    const int smem2 = fixed + n_kv * 2 * SK * 128;
-    static int dev2 = -1;
-    if (dev2 != dev) {
-      EVT_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      dev2 = dev;
-    }
-    EVT_CUDA(launch_pdl(attention2_kernel, dim3(grid), dim3(kThreads2), smem2, stream,
-                        pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, tmO, q));
-    EVT_LAUNCH_CHECK("attention2_kernel");
-    return EVT_OK;
-  }
+  CUtensorMap tmKV;
+  int rc = make_tmap_2d(&tmKV, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), SK, kHD);
+  if (rc != EVT_OK) return rc;
 #ifdef EVT_EXPERIMENTAL
-  static const int pp_mode = getenv("EVT_ATTN_PP") != nullptr ? atoi(getenv("EVT_ATTN_PP")) : 0;  // 1 / 2 threads per row
-  if (pp_mode != 0 && SK <= kPPSCols && smem + 2048 <= max_smem) {
-    static int pp_dev = -1;
-    if (pp_dev != dev) {
+  // round-1 kernels, selectable for A/B timing: EVT_ATTN_V1=1 (two softmax groups, one issuer), EVT_ATTN_PP=1|2 (ping-pong)
+  static const bool use_v1 = getenv("EVT_ATTN_V1") != nullptr && atoi(getenv("EVT_ATTN_V1")) != 0;
+  static const int pp_mode = getenv("EVT_ATTN_PP") != nullptr ? atoi(getenv("EVT_ATTN_PP")) : 0;
+  if (use_v1 || pp_mode != 0) {
+    CUtensorMap tmQ;
+    rc = make_tmap_2d(&tmQ, qkv, 2, rows, 3ull * heads * kHD, static_cast<uint64_t>(ldq), kQRows, kHD);
+    if (rc != EVT_OK) return rc;
+    AttnParams p;
+    p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+    p.head_mask = head_mask;
+    p.ldc = ldc;
+    p.S = S;
+    p.SK = SK;
+    p.heads = heads;
+    p.B = B;
+    p.q_tiles = q_tiles;
+    p.n_mt = n_mt;
+    p.scale_log2e = scale_log2e;
+    const int stage_bytes = kQRows * 128 + 2 * SK * 128;
+    const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
+    int n_stages = (max_smem - 1024 - bar_bytes) / stage_bytes;
+    if (n_stages > kMaxStages) n_stages = kMaxStages;
+    if (n_stages < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two shared-memory stages");
+    p.n_stages = n_stages;
+    const int smem = 1024 + n_stages * stage_bytes + bar_bytes;
+    static int configured_dev = -1;
+    if (configured_dev != dev) {
+      EVT_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       EVT_CUDA(cudaFuncSetAttribute(attention_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      pp_dev = dev;
+      configured_dev = dev;
     }
-    const bool pdl = pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD);
-    if (pp_mode == 2)
-      EVT_CUDA(launch_pdl(attention_pp_kernel<2>, dim3(grid), dim3(32 * 10), smem + 2048, stream, pdl, tmQ, tmKV, p));
-    else
-      EVT_CUDA(launch_pdl(attention_pp_kernel<1>, dim3(grid), dim3(32 * 6), smem + 2048, stream, pdl, tmQ, tmKV, p));
-    EVT_LAUNCH_CHECK("attention_pp_kernel");
+    if (pp_mode != 0 && SK <= kPPSCols && smem + 2048 <= max_smem) {
+      if (pp_mode == 2)
+        EVT_CUDA(launch_pdl(attention_pp_kernel<2>, dim3(grid), dim3(32 * 10), smem + 2048, stream, pdl, tmQ, tmKV, p));
+      else
+        EVT_CUDA(launch_pdl(attention_pp_kernel<1>, dim3(grid), dim3(32 * 6), smem + 2048, stream, pdl, tmQ, tmKV, p));
+      EVT_LAUNCH_CHECK("attention_pp_kernel");
+      return EVT_OK;
+    }
+    EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl, tmQ, tmKV, p));
+    EVT_LAUNCH_CHECK("attention_kernel");
     return EVT_OK;
   }
 #endif  // EVT_EXPERIMENTAL
-  EVT_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(kThreadsP), smem, stream, pdl_for_work(static_cast<long long>(B) * S, static_cast<long long>(heads) * kHD), tmQ, tmKV, p));
-  EVT_LAUNCH_CHECK("attention_kernel");
+  CUtensorMap tmO, tmQ;
+  rc = make_tmap_3d_rows(&tmQ, qkv, 2, 3ull * heads * kHD, static_cast<uint64_t>(S), static_cast<uint64_t>(B),
+                         static_cast<uint64_t>(ldq), 32, kHD);
+  if (rc != EVT_OK) return rc;
+  rc = make_tmap_3d_rows(&tmO, ctx, 2, static_cast<uint64_t>(heads) * kHD, static_cast<uint64_t>(S), static_cast<uint64_t>(B),
+                         static_cast<uint64_t>(ldc), 32, kHD);
+  if (rc != EVT_OK) return rc;
+  Attn2Params q;
+  q.head_mask = head_mask;
+  q.S = S;
+  q.SK = SK;
+  q.heads = heads;
+  q.B = B;
+  q.n_mt = n_mt;
+  q.q_tiles = q_tiles;
+  q.scale_log2e = scale_log2e;
+  static const bool no_rot = getenv("EVT_ATTN_NOROT") != nullptr && atoi(getenv("EVT_ATTN_NOROT")) != 0;  // A/B timing
+  q.rot_mask = no_rot ? 0 : 3;
+  const int fixed = 1024 + 2 * kQTileBytes + kSoftmaxWarps * kStgWarpBytes + (2 * kMaxKV + 12) * 8 + 16;
+  int n_kv = (max_smem - fixed) / (2 * SK * 128);
+  if (n_kv > kMaxKV) n_kv = kMaxKV;
+  if (n_kv < 2) return fail(EVT_ERR_UNSUPPORTED, "attention: sequence too long for two K/V stages");
+  q.n_kv = n_kv;
+  const int smem2 = fixed + n_kv * 2 * SK * 128;
+  static int dev2 = -1;
+  if (dev2 != dev) {
+    EVT_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    dev2 = dev;
+  }
+  EVT_CUDA(launch_pdl(attention2_kernel, dim3(grid), dim3(kThreads2), smem2, stream, pdl, tmQ, tmKV, tmO, q));
+  EVT_LAUNCH_CHECK("attention2_kernel");
   return EVT_OK;
 }
 

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
       const float2 b = *reinterpret_cast<const float2*>(beta + c);
       float o0 = (v[i].x - mean) * rstd * g.x + b.x;
       float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      // the f32 copy (TF dialect: it becomes the skip connection) keeps full precision; only the GEMM operand is rounded
+      if (y_copy != nullptr) *reinterpret_cast<float2*>(y_copy + row * x_stride + c) = make_float2(o0, o1);
       if (OUT == EVT_TF32) {
         o0 = ptx::round_tf32(o0);
         o1 = ptx::round_tf32(o1);
@@ -71,7 +73,6 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, long long 
       } else {
         *reinterpret_cast<float2*>(reinterpret_cast<float*>(y) + row * y_stride + c) = make_float2(o0, o1);
       }
-      if (y_copy != nullptr) *reinterpret_cast<float2*>(y_copy + row * x_stride + c) = make_float2(o0, o1);
     }
   }
 }
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long
       float o1 = (v[i].y - mean) * rstd * g.y + b.y;
       float o2 = (v[i].z - mean) * rstd * g.z + b.z;
       float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y_copy != nullptr) *reinterpret_cast<float4*>(y_copy + row * x_stride + c) = make_float4(o0, o1, o2, o3);  // unrounded
       if (OUT == EVT_TF32) {
         o0 = ptx::round_tf32(o0);
         o1 = ptx::round_tf32(o1);
@@ -153,7 +155,6 @@ __global__ void __launch_bounds__(256) ln_rows4_kernel(const float* x, long long
       } else {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * y_stride + c) = make_float4(o0, o1, o2, o3);
       }
-      if (y_copy != nullptr) *reinterpret_cast<float4*>(y_copy + row * x_stride + c) = make_float4(o0, o1, o2, o3);
     }
   }
 }
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(256) ln_rows4_sub_kernel(const float* x, long 
     float o1 = (v[i].y - mean) * rstd * g.y + b.y;
     float o2 = (v[i].z - mean) * rstd * g.z + b.z;
     float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y_copy != nullptr) *reinterpret_cast<float4*>(y_copy + row * x_stride + c) = make_float4(o0, o1, o2, o3);  // unrounded
     if (OUT == EVT_TF32) {
       o0 = ptx::round_tf32(o0);
       o1 = ptx::round_tf32(o1);
@@ -222,7 +224,6 @@ __global__ void __launch_bounds__(256) ln_rows4_sub_kernel(const float* x, long 
     } else {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * y_stride + c) = make_float4(o0, o1, o2, o3);
     }
-    if (y_copy != nullptr) *reinterpret_cast<float4*>(y_copy + row * x_stride + c) = make_float4(o0, o1, o2, o3);
   }
 }
 
@@ -250,10 +251,10 @@ __global__ void __launch_bounds__(256) ln_rows_generic_kernel(const float* x, lo
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
   for (int c = lane; c < D; c += 32) {
     float o = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if (y_copy != nullptr) y_copy[row * x_stride + c] = o;  // unrounded
     if (OUT == EVT_TF32) o = ptx::round_tf32(o);
     if (OUT == EVT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[row * y_stride + c] = __float2bfloat16_rn(o);
     else reinterpret_cast<float*>(y)[row * y_stride + c] = o;
-    if (y_copy != nullptr) y_copy[row * x_stride + c] = o;
   }
 }
 

@@ -21,9 +21,9 @@ class PipelinedClassifier:
         self.model = model
         self.chunk = int(chunk)
         self.device = next(model.parameters()).device
-        c = model.config
-        self._bufs = [torch.empty((self.chunk, 3, c.image_size, c.image_size), dtype=torch.float32, device=self.device)
-                      for _ in range(2)]
+        # device staging buffers, per pixel storage type: the host batch is copied as it is (f32, bf16 or raw uint8) and the
+        # conversion happens inside the library's patch gather, so bf16 / u8 loaders move 2x / 4x fewer bytes over PCIe
+        self._bufs_by_dtype = {}
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._free = [torch.cuda.Event() for _ in range(2)]
@@ -36,6 +36,13 @@ class PipelinedClassifier:
             raise ValueError("PipelinedClassifier takes host tensors; call the model directly for device tensors")
         B = host_pixels.shape[0]
         c = self.model.config
+        if host_pixels.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            host_pixels = host_pixels.float()
+        bufs = self._bufs_by_dtype.get(host_pixels.dtype)
+        if bufs is None:
+            bufs = self._bufs_by_dtype[host_pixels.dtype] = [
+                torch.empty((self.chunk, 3, c.image_size, c.image_size), dtype=host_pixels.dtype, device=self.device)
+                for _ in range(2)]
         main = torch.cuda.current_stream(self.device)
         out = torch.empty((B, c.num_labels) if want_logits else (B,), dtype=torch.float32 if want_logits else torch.int64,
                           device=self.device)
@@ -59,10 +66,10 @@ class PipelinedClassifier:
             k = i & 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._free[k])          # buffer k no longer read by forward i-2
-                self._bufs[k][: e - s].copy_(host_pixels[s:e], non_blocking=True)
+                bufs[k][: e - s].copy_(host_pixels[s:e], non_blocking=True)
                 self._ready[k].record(self._copy_stream)
             main.wait_event(self._ready[k])
-            lg = self.model(self._bufs[k][: e - s]).logits
+            lg = self.model(bufs[k][: e - s]).logits
             if want_logits:
                 out[s:e] = lg
                 if host_out is not None:

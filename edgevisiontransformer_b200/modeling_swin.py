@@ -222,9 +222,14 @@ class B200SwinForImageClassification(nn.Module):
         return ops.linear(pooled, self.w_cls, self.b_cls, out_dtype=torch.float32)
 
     @torch.no_grad()
-    def forward(self, pixel_values: torch.Tensor = None, labels=None, **ignored) -> ImageClassifierOutput:
+    def forward(self, pixel_values: torch.Tensor = None, head_mask=None, labels=None, output_attentions=None,
+                output_hidden_states=None, interpolate_pos_encoding=None, return_dict=None) -> ImageClassifierOutput:
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
+        for name, v in (("head_mask", head_mask), ("labels", labels), ("output_attentions", output_attentions),
+                        ("output_hidden_states", output_hidden_states), ("interpolate_pos_encoding", interpolate_pos_encoding)):
+            if v is not None and v is not False:
+                raise NotImplementedError(f"B200SwinForImageClassification.forward does not support {name}")
         x = pixel_values
         if not x.is_cuda:
             raise RuntimeError("pixel_values must be a CUDA tensor (no CPU fallback); move the batch with .to(device)")

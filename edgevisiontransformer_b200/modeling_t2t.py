@@ -95,6 +95,9 @@ class B200T2TViT(nn.Module):
             head_size=D // num_heads, embed_k=sd["t2t.project.kernel"].shape[0], precision=precision)
         self.config = self.core.config
         self._graphs: dict = {}
+        # The graphs captured by forward_graphed bake in the core's activation workspace pointer: drop them whenever the core
+        # reallocates it (a larger batch arrived), or a replay would write into memory already returned to the allocator.
+        self.core.on_workspace_realloc(self._graphs.clear)
         self.eval()
 
     @torch.no_grad()

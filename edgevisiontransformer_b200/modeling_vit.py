@@ -61,7 +61,12 @@ class ImageClassifierOutput:
 
 
 _ACT = {"gelu": _lib.ACT_GELU_ERF, "gelu_erf": _lib.ACT_GELU_ERF, "gelu_new": _lib.ACT_GELU_TANH,
-        "gelu_tanh": _lib.ACT_GELU_TANH, "gelu_pytorch_tanh": _lib.ACT_GELU_TANH, "tanh": _lib.ACT_GELU_TANH}
+        "gelu_tanh": _lib.ACT_GELU_TANH, "gelu_pytorch_tanh": _lib.ACT_GELU_TANH}
+# ("tanh" is deliberately absent: in HF's ACT2FN it names plain nn.Tanh, not the tanh-approximate GELU.)
+
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)   # timm.data.constants, used by deit_pruning/src/utils.py:106-107
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+_PIX = {torch.float32: _lib.PIX_F32, torch.bfloat16: _lib.PIX_BF16, torch.uint8: _lib.PIX_U8}
 
 
 def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12, hidden_act="gelu", head_size=64,
@@ -114,7 +119,14 @@ class B200ViTForImageClassification(nn.Module):
         self._ws2: Optional[torch.Tensor] = None
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[int, tuple] = {}
+        self._ws_listeners: List = []      # called when the workspace is reallocated (dependent CUDA graphs must be dropped)
         self._profiling = False
+        # uint8 pixels are normalised inside the patch gather: (x / 255 - mean) / std, the reference loader's transform
+        self.pixel_mean: Tuple[float, float, float] = IMAGENET_DEFAULT_MEAN
+        self.pixel_std: Tuple[float, float, float] = IMAGENET_DEFAULT_STD
+        self._head_mask: Optional[torch.Tensor] = None     # [L, max heads] f32 on the device, set by mask_heads()
+        self._capture_ctx = False
+        self.context_layers: List[Optional[torch.Tensor]] = []   # per layer [B, heads_l, tokens, 64] after a capturing forward
         spec = _lib.ModelSpec()
         spec.dialect = _lib.DIALECT_TF if config.dialect == "tf" else _lib.DIALECT_HF
         spec.hidden, spec.layers, spec.tokens = config.hidden_size, config.num_hidden_layers, config.tokens
@@ -245,14 +257,81 @@ class B200ViTForImageClassification(nn.Module):
             self._ws = torch.empty(n.value, dtype=torch.uint8, device=self._device)
             self._ws_batch = batch
             self._graphs.clear()
+            for cb in self._ws_listeners:    # graphs captured by wrappers (T2T front-end) hold the old workspace pointer
+                cb()
         return self._ws
 
-    def _run(self, pixels: torch.Tensor, logits: torch.Tensor, ws: Optional[torch.Tensor] = None) -> None:
+    def on_workspace_realloc(self, callback) -> None:
+        """Register a callable invoked whenever the activation workspace is reallocated: anything that baked the old
+        pointer into a CUDA graph (modeling_t2t.B200T2TViT.forward_graphed) must drop it."""
+        self._ws_listeners.append(callback)
+
+    def _run(self, pixels: torch.Tensor, logits: torch.Tensor, ws: Optional[torch.Tensor] = None,
+             head_mask: Optional[torch.Tensor] = None, ctx: Optional[List[torch.Tensor]] = None) -> None:
         B = pixels.shape[0]
         if ws is None:
             ws = self._workspace(B)
-        _lib.check(self._lib.evt_model_forward(self._handle, pixels.data_ptr(), B, logits.data_ptr(), ws.data_ptr(),
-                                               ws.numel(), torch.cuda.current_stream().cuda_stream), "model_forward")
+        stream = torch.cuda.current_stream().cuda_stream
+        if pixels.dtype == torch.float32 and head_mask is None and ctx is None:
+            _lib.check(self._lib.evt_model_forward(self._handle, pixels.data_ptr(), B, logits.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), stream), "model_forward")
+            return
+        opts = _lib.ForwardOpts()
+        opts.pixel_dtype = _PIX[pixels.dtype]
+        for c in range(3):
+            opts.pixel_scale[c] = 1.0 / (255.0 * self.pixel_std[c])
+            opts.pixel_bias[c] = -self.pixel_mean[c] / self.pixel_std[c]
+        if head_mask is not None:
+            opts.head_mask = head_mask.data_ptr()
+            opts.head_mask_ld = head_mask.stride(0)
+        if ctx is not None:
+            arr = (C.c_void_p * len(ctx))(*[t.data_ptr() for t in ctx])
+            opts.ctx_out = C.cast(arr, C.POINTER(C.c_void_p))
+        _lib.check(self._lib.evt_model_forward_ex(self._handle, pixels.data_ptr(), C.byref(opts), B, logits.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), stream), "model_forward_ex")
+
+    # ------------------------------------------------------------------ are_16_heads surface
+    @property
+    def vit(self):
+        """`model.vit.mask_heads(to_prune)` is how are_16_heads/run_classifier.py:247-250 reaches the encoder."""
+        return self
+
+    def mask_heads(self, heads_to_mask: Optional[Dict[int, object]]) -> None:
+        """Zero the context of the given heads, {layer: iterable of head indices}, in every later forward (the heads stay
+        in the weights: are_16_heads' masking-instead-of-pruning mode).  None or {} clears the mask."""
+        if not heads_to_mask:
+            self._head_mask = None
+            return
+        c = self.config
+        m = torch.ones((c.num_hidden_layers, max(c.heads)), dtype=torch.float32)
+        for layer, hs in heads_to_mask.items():
+            for h in hs:
+                if not (0 <= int(layer) < c.num_hidden_layers and 0 <= int(h) < c.heads[int(layer)]):
+                    raise ValueError(f"mask_heads: head {h} of layer {layer} does not exist")
+                m[int(layer), int(h)] = 0.0
+        self._head_mask = m.to(self._device)
+
+    def capture_context(self, enable: bool = True) -> None:
+        """Keep every layer's attention context of the next forwards in `context_layers[l]` ([B, heads_l, tokens, 64],
+        the `context_layer_val` that are_16_heads/classifier_eval.py:183-191 reads for the head-importance score)."""
+        self._capture_ctx = bool(enable)
+        if not enable:
+            self.context_layers = []
+
+    def _resolve_head_mask(self, head_mask) -> Optional[torch.Tensor]:
+        """HF semantics (get_head_mask): [heads] applies to every layer, [layers, heads] per layer; multiplied into the
+        attention probabilities of a head, i.e. into its context.  Combined with mask_heads()."""
+        c = self.config
+        hm = self._head_mask
+        if head_mask is not None:
+            m = torch.as_tensor(head_mask, dtype=torch.float32, device=self._device)
+            if m.dim() == 1:
+                m = m.unsqueeze(0).expand(c.num_hidden_layers, -1)
+            if m.dim() != 2 or m.shape[0] != c.num_hidden_layers or m.shape[1] < max(c.heads):
+                raise ValueError(f"head_mask must be [heads] or [layers, heads] with heads >= {max(c.heads)}")
+            m = m[:, :max(c.heads)]
+            hm = m if hm is None else hm * m
+        return hm.contiguous() if hm is not None else None
 
     def _run_chunks_two_streams(self, x: torch.Tensor, logits: torch.Tensor) -> None:
         """Even chunks on the current stream, odd chunks on a side stream with a second workspace."""
@@ -274,27 +353,43 @@ class B200ViTForImageClassification(nn.Module):
         main.wait_stream(side)
 
     @torch.no_grad()
-    def forward(self, pixel_values: Optional[torch.Tensor] = None, labels=None, **ignored) -> ImageClassifierOutput:
+    def forward(self, pixel_values: Optional[torch.Tensor] = None, head_mask=None, labels=None, output_attentions=None,
+                output_hidden_states=None, interpolate_pos_encoding=None, return_dict=None) -> ImageClassifierOutput:
+        """HF `ViTForImageClassification.forward` surface (SITE/models/vit/modeling_vit.py:620-653).  pixel_values may be
+        f32, bf16 or uint8 (uint8 is normalised with pixel_mean / pixel_std inside the patch gather).  Options this
+        inference path does not implement raise instead of being ignored."""
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
+        for name, v in (("labels", labels), ("output_attentions", output_attentions),
+                        ("output_hidden_states", output_hidden_states), ("interpolate_pos_encoding", interpolate_pos_encoding)):
+            if v is not None and v is not False:
+                raise NotImplementedError(f"B200ViTForImageClassification.forward does not support {name}")
         x = pixel_values
         if not x.is_cuda:
             raise RuntimeError("pixel_values must be a CUDA tensor (no CPU fallback); move the batch with .to(device)")
         c = self.config
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != c.image_size or x.shape[3] != c.image_size:
             raise ValueError(f"Input image size ({tuple(x.shape[2:])}) doesn't match model ({c.image_size}*{c.image_size}).")
-        if x.dtype != torch.float32:
+        if x.dtype not in _PIX:
             x = x.float()
         x = x.contiguous()
         B = x.shape[0]
         logits = torch.empty((B, c.num_labels), dtype=torch.float32, device=x.device)
+        hm = self._resolve_head_mask(head_mask)
+        ctx_all = None
+        if self._capture_ctx:
+            cdt = torch.float32 if c.precision == "tf32" else torch.bfloat16
+            ctx_all = [torch.empty((B * c.tokens, h * c.head_size), dtype=cdt, device=x.device) for h in c.heads]
         with torch.cuda.device(self._device):
-            if self.concurrent_chunks >= 2 and B > self.max_batch and not self._profiling:
+            if self.concurrent_chunks >= 2 and B > self.max_batch and not self._profiling and hm is None and ctx_all is None:
                 self._run_chunks_two_streams(x, logits)
             else:
                 for s in range(0, B, self.max_batch):
                     e = min(B, s + self.max_batch)
-                    self._run(x[s:e], logits[s:e])
+                    ctx = [t[s * c.tokens:e * c.tokens] for t in ctx_all] if ctx_all is not None else None
+                    self._run(x[s:e], logits[s:e], head_mask=hm, ctx=ctx)
+        if ctx_all is not None:
+            self.context_layers = [t.view(B, c.tokens, h, c.head_size).permute(0, 2, 1, 3) for t, h in zip(ctx_all, c.heads)]
         return ImageClassifierOutput(logits=logits)
 
     @torch.no_grad()
@@ -326,7 +421,7 @@ class B200ViTForImageClassification(nn.Module):
         """Same result as forward(); the launch sequence for this batch size is captured once in a CUDA graph
         and replayed, removing per-kernel launch overhead at small batch."""
         B = pixel_values.shape[0]
-        if B > self.max_batch:
+        if B > self.max_batch or self._head_mask is not None or self._capture_ctx:
             return self.forward(pixel_values)
         ent = self._graphs.get(B)
         with torch.cuda.device(self._device):
@@ -375,14 +470,21 @@ def _first(v):
 
 
 def normalise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Accept HF ViT ('vit.'), HF DeiT ('deit.') and DDP ('module.') prefixes; 'cls_classifier' -> 'classifier'."""
+    """Accept HF ViT ('vit.'), HF DeiT ('deit.') and DDP ('module.') prefixes.
+
+    HF `DeiTForImageClassification` (198 tokens: cls + distillation token, ONE classifier on the cls row,
+    SITE/models/deit/modeling_deit.py:595-659) loads as it is.  `DeiTForImageClassificationWithTeacher` does not: its
+    logits are the mean of `cls_classifier(cls row)` and `distillation_classifier(distillation row)`, a second head this
+    runtime does not have -- such a checkpoint is refused rather than answered from the cls head alone."""
+    if any(k.split("module.")[-1].startswith(("distillation_classifier.", "cls_classifier.")) for k in sd):
+        raise ValueError("distilled DeiT checkpoint (DeiTForImageClassificationWithTeacher: cls_classifier + "
+                         "distillation_classifier, logits averaged over two heads) is not supported; load "
+                         "ViTForImageClassification / DeiTForImageClassification weights")
     out = {}
     for k, v in sd.items():
         if k.startswith("module."):
             k = k[len("module."):]
         if k.startswith("deit."):
             k = "vit." + k[len("deit."):]
-        if k.startswith("cls_classifier."):
-            k = "classifier." + k[len("cls_classifier."):]
         out[k] = v
     return out

@@ -12,7 +12,8 @@ from . import _lib
 from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EVT_BF16, EVT_F32  # noqa: F401
 
 ACTS = {None: ACT_NONE, "none": ACT_NONE, "gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF, "erf": ACT_GELU_ERF,
-        "gelu_tanh": ACT_GELU_TANH, "tanh": ACT_GELU_TANH, "gelu_new": ACT_GELU_TANH}
+        "gelu_tanh": ACT_GELU_TANH, "gelu_new": ACT_GELU_TANH, "gelu_pytorch_tanh": ACT_GELU_TANH}
+# "tanh" is not an alias: HF's ACT2FN["tanh"] is plain nn.Tanh, which the fused epilogue does not implement.
 
 
 def _stream() -> int:

@@ -53,8 +53,13 @@ def embeddings(sd: Dict[str, torch.Tensor], x: torch.Tensor, spec: ViTSpec) -> t
     return h + sd["vit.embeddings.position_embeddings"]
 
 
-def attention(q, k, v, head_size: int):
-    """eager_attention_forward, SITE/models/vit/modeling_vit.py:171-196."""
+def attention(q, k, v, head_size: int, head_mask: Optional[torch.Tensor] = None, return_heads: bool = False):
+    """eager_attention_forward, SITE/models/vit/modeling_vit.py:171-196.
+
+    head_mask [heads]: `attention_probs = attention_probs * head_mask` of the pinned transformers 4.7.0
+    (ViTSelfAttention.forward; the argument was dropped from later releases) -- what are_16_heads' `mask_heads`
+    (are_16_heads/run_classifier.py:247-250) sets to 0 for masked heads.  return_heads: also return the per-head context
+    [B, heads, S, head_size], the `context_layer_val` of are_16_heads/classifier_eval.py:183-191."""
     B, S, A = q.shape
     nh = A // head_size
 
@@ -64,11 +69,15 @@ def attention(q, k, v, head_size: int):
     q, k, v = split(q), split(k), split(v)
     scores = torch.matmul(q, k.transpose(-1, -2)) * (head_size ** -0.5)
     probs = torch.softmax(scores, dim=-1)
+    if head_mask is not None:
+        probs = probs * head_mask.to(probs.dtype).view(1, nh, 1, 1)
     ctx = torch.matmul(probs, v)
-    return ctx.transpose(1, 2).reshape(B, S, A)
+    out = ctx.transpose(1, 2).reshape(B, S, A)
+    return (out, ctx) if return_heads else out
 
 
-def encoder_layer(sd: Dict[str, torch.Tensor], l: int, x: torch.Tensor, spec: ViTSpec) -> torch.Tensor:
+def encoder_layer(sd: Dict[str, torch.Tensor], l: int, x: torch.Tensor, spec: ViTSpec,
+                  head_mask: Optional[torch.Tensor] = None, ctx_out: Optional[list] = None) -> torch.Tensor:
     """ViTLayer.forward, SITE/models/vit/modeling_vit.py:328-346 (pre-LN)."""
     p = f"vit.encoder.layer.{l}."
     D = spec.hidden
@@ -77,7 +86,9 @@ def encoder_layer(sd: Dict[str, torch.Tensor], l: int, x: torch.Tensor, spec: Vi
     q = F.linear(y, sd[p + "attention.attention.query.weight"], sd[p + "attention.attention.query.bias"])
     k = F.linear(y, sd[p + "attention.attention.key.weight"], sd[p + "attention.attention.key.bias"])
     v = F.linear(y, sd[p + "attention.attention.value.weight"], sd[p + "attention.attention.value.bias"])
-    ctx = attention(q, k, v, spec.head_size)
+    ctx, heads_ctx = attention(q, k, v, spec.head_size, head_mask, return_heads=True)
+    if ctx_out is not None:
+        ctx_out.append(heads_ctx)
     x = x + F.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"])
     y = F.layer_norm(x, (D,), sd[p + "layernorm_after.weight"], sd[p + "layernorm_after.bias"], spec.eps)
     h = act(F.linear(y, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
@@ -86,12 +97,16 @@ def encoder_layer(sd: Dict[str, torch.Tensor], l: int, x: torch.Tensor, spec: Vi
 
 @torch.no_grad()
 def vit_forward(sd: Dict[str, torch.Tensor], spec: ViTSpec, pixel_values: torch.Tensor,
-                return_hidden: bool = False):
-    """ViTForImageClassification.forward, SITE/models/vit/modeling_vit.py:620-653 -> logits [B, num_labels]."""
+                return_hidden: bool = False, head_mask: Optional[torch.Tensor] = None, ctx_out: Optional[list] = None):
+    """ViTForImageClassification.forward, SITE/models/vit/modeling_vit.py:620-653 -> logits [B, num_labels].
+
+    head_mask [layers, >= max heads] (row l applies to the heads of layer l); ctx_out: a list that receives every layer's
+    per-head context [B, heads_l, S, head_size]."""
     x = embeddings(sd, pixel_values.to(torch.float32), spec)
     hidden = [x]
     for l in range(spec.layers):
-        x = encoder_layer(sd, l, x, spec)
+        hm = head_mask[l, :spec.heads[l]] if head_mask is not None else None
+        x = encoder_layer(sd, l, x, spec, hm, ctx_out)
         hidden.append(x)
     x = F.layer_norm(x, (spec.hidden,), sd["vit.layernorm.weight"], sd["vit.layernorm.bias"], spec.eps)
     logits = F.linear(x[:, 0, :], sd["classifier.weight"], sd["classifier.bias"])

@@ -65,6 +65,16 @@ def test_zero_heads_without_config_entry_and_all_zero_ffn():
 
 
 def test_key_normalisation():
-    sd = {"module.deit.embeddings.cls_token": torch.zeros(1, 1, 8), "cls_classifier.weight": torch.zeros(2, 8)}
+    sd = {"module.deit.embeddings.cls_token": torch.zeros(1, 1, 8), "module.classifier.weight": torch.zeros(2, 8)}
     out = normalise_keys(sd)
     assert set(out) == {"vit.embeddings.cls_token", "classifier.weight"}
+
+
+def test_distilled_deit_checkpoint_is_refused():
+    """DeiTForImageClassificationWithTeacher averages two heads (cls + distillation row); answering from the cls head
+    alone would be silently wrong, so the loader refuses the layout (the timm path refuses head_dist the same way)."""
+    import pytest
+    for extra in ("cls_classifier.weight", "distillation_classifier.weight", "module.distillation_classifier.bias"):
+        sd = {"deit.embeddings.cls_token": torch.zeros(1, 1, 8), extra: torch.zeros(2, 8)}
+        with pytest.raises(ValueError, match="distilled DeiT"):
+            normalise_keys(sd)

@@ -152,14 +152,19 @@ def test_gemm_residual_layernorm_fused(M, N, K):
     want_res = res0 + a[:, :K].float() @ w[:, :K].float().t() + bias
     want_xn = torch.nn.functional.layer_norm(want_res, (N,), gamma, beta, eps)
     res = res0.clone()
-    xn = ops.linear_residual_layernorm(a, w, bias, res, gamma, beta, eps, k=K)
-    torch.cuda.synchronize()
     unfused = res0.clone()
     try:
-        ops.set_gemm_pair_mode(0)           # forced kernel choice: no split K, deterministic accumulation order
+        # Deterministic accumulation order on both sides: by default the entry point issues the residual GEMM and the
+        # LayerNorm kernel (the single-kernel version is an EVT_EXPERIMENTAL build option), and a small-M residual GEMM
+        # splits K over idle SMs, whose reduce-adds land in any order.
+        ops.set_gemm_split_k(False)
+        xn = ops.linear_residual_layernorm(a, w, bias, res, gamma, beta, eps, k=K)
+        torch.cuda.synchronize()
+        ops.set_gemm_pair_mode(0)           # forced kernel choice: the 1-CTA kernel
         ops.linear(a, w, bias, residual=unfused, out=unfused, out_dtype=torch.float32, k=K)
     finally:
         ops.set_gemm_pair_mode(-1)
+        ops.set_gemm_split_k(True)
     assert torch.equal(res, unfused)
     assert (res - want_res).abs().max().item() < 2e-3 * max(1.0, math.sqrt(K) * 0.05)
     ref_xn = torch.nn.functional.layer_norm(res, (N,), gamma, beta, eps)
@@ -174,7 +179,9 @@ def test_gemm_residual_layernorm_constant_rows():
     M, N, K = 300, 768, 64
     a = _rand((M, K), 1).bfloat16()
     w = torch.zeros((N, K), dtype=torch.bfloat16, device="cuda")
-    res = (_rand((M, 1), 2) * 100).expand(M, N).contiguous()
+    # constants whose 768-term sums are exact in f32 (multiples of 1/4 up to 64): the mean is then exact for any
+    # summation order, which is what "exactly constant" needs with eps = 1e-12
+    res = (torch.round(_rand((M, 1), 2) * 100).clamp(-256, 256) / 4).expand(M, N).contiguous()
     gamma = 1 + _rand((N,), 3, 0.1)
     beta = _rand((N,), 4, 0.1)
     xn = ops.linear_residual_layernorm(a, w, None, res, gamma, beta, 1e-12)

@@ -187,3 +187,68 @@ def test_swin_host_tables_and_key_adapter():
     assert set(back) == keys
     for k in keys:
         assert torch.equal(back[k], sd[k]), k
+
+
+def test_head_mask_restatement_matches_hf_with_scaled_value_heads():
+    """transformers 4.7.0 multiplies a head's attention probabilities by head_mask[l, h]; the installed release no longer
+    takes the argument, so the restatement is pinned through an identity: probs * m @ v == probs @ (m * v), i.e. the live HF
+    module with the value projection of head h scaled by m (weights and bias) must give the masked oracle's logits.  The
+    per-head contexts the oracle returns are pinned the same way (the unmasked ones against a forward hook on the module)."""
+    spec = ViTSpec.deit("tiny", layers=3, heads=[3] * 3, inter=[768] * 3)
+    model = ovit.build_hf_model(spec, seed=4, stress=True)
+    sd = ovit.state_dict_of(model)
+    x = ovit.synthetic_images(2, seed=5)
+    mask = torch.tensor([[1.0, 0.0, 1.0], [0.5, 1.0, 0.0], [1.0, 1.0, 1.0]])
+    ctxs = []
+    got = ovit.vit_forward(sd, spec, x, head_mask=mask, ctx_out=ctxs)
+    assert [tuple(c.shape) for c in ctxs] == [(2, 3, 197, 64)] * 3
+    with torch.no_grad():
+        for l in range(3):
+            v = model.vit.encoder.layer[l].attention.attention.value
+            scale = mask[l].repeat_interleave(64)
+            v.weight.mul_(scale[:, None])
+            v.bias.mul_(scale)
+        want = model(pixel_values=x).logits
+    assert (got - want).abs().max() < 5e-5
+    # a masked head (m = 0) is equivalent to the pruned model of the pinned pruning restatement
+    base = ovit.vit_forward(sd, spec, x)
+    assert (got - base).abs().max() > 1e-3      # the mask does something
+
+
+def test_deit_198_token_restatement_matches_hf():
+    """HF `DeiTForImageClassification` (cls + distillation token, one classifier on the cls row,
+    SITE/models/deit/modeling_deit.py:595-659): the oracle's 198-token branch against the live module."""
+    from transformers import DeiTConfig, DeiTForImageClassification
+    cfg = DeiTConfig(hidden_size=192, num_hidden_layers=2, num_attention_heads=3, intermediate_size=768, num_labels=10,
+                     attn_implementation="eager")
+    torch.manual_seed(9)
+    model = DeiTForImageClassification(cfg).eval()
+    with torch.no_grad():
+        model.deit.embeddings.cls_token.normal_(0, 0.02)
+        model.deit.embeddings.distillation_token.normal_(0, 0.02)
+        model.deit.embeddings.position_embeddings.normal_(0, 0.02)
+    sd = {k.replace("deit.", "vit.", 1) if k.startswith("deit.") else k: v.detach().float() for k, v in model.state_dict().items()}
+    spec = ViTSpec(hidden=192, layers=2, heads=[3, 3], inter=[768, 768], tokens=198, num_labels=10)
+    x = ovit.synthetic_images(2, seed=3)
+    got = ovit.vit_forward(sd, spec, x)
+    with torch.no_grad():
+        want = model(pixel_values=x).logits
+    assert (got - want).abs().max() < 5e-5
+
+
+def test_two_independent_t2t_front_end_restatements_agree():
+    """oracle/t2t.py (torch: unfold / einsum) against oracle/t2t_np.py (NumPy float64, explicit index arithmetic, written
+    separately from the reference's text): a shared misreading of tf_Unfold's depth order, of the k | q | v split or of the
+    performer algebra would have to be made twice.  Parity of both stays unpinned (no TensorFlow in the image)."""
+    from oracle import t2t_np
+    sd = ot2t.init_t2t_vit(hidden=64, depth=1, num_heads=1, mlp_ratio=2.0, seed=5, stress=True)
+    x = ovit.synthetic_images(1, seed=6, channels_last=True)
+    a = ot2t.t2t_module(sd, x).double().numpy()
+    b = t2t_np.t2t_tokens(sd, x)
+    assert a.shape == b.shape == (1, 196, 64)
+    assert np.abs(a - b).max() < 2e-4 * max(1.0, np.abs(b).max())
+    # the soft split alone is bit-level: a gather
+    u = ot2t.unfold_nhwc(x, 7, 4, 2).double().numpy()
+    assert np.array_equal(u, t2t_np.soft_split(x.double().numpy(), 7, 4, 2))
+    y = torch.randn(1, 28, 28, 8, generator=torch.Generator().manual_seed(1))
+    assert np.array_equal(ot2t.unfold_nhwc(y, 3, 2, 1).double().numpy(), t2t_np.soft_split(y.double().numpy(), 3, 2, 1))
