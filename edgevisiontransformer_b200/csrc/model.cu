@@ -441,11 +441,20 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
     const int a = lw.a;
-    if (!xn_ready)
-      EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+    // Narrow residual streams at large batch (D <= 384: DeiT-Tiny / -Small, T2T): the LayerNorm runs inside the projection
+    // that consumes it, as the producer of its A operand (gemm_ln.cu) -- 5 launches per layer instead of 7, and the bf16
+    // copy of the normalised rows never goes to HBM.
+    const bool ln_in_gemm = !tf32 && !fuse_ln && gemm_ln_supported(M, 3 * a, D);
+    if (ln_in_gemm) {
+      EVT_STAGE(EVT_STAGE_QKV, gemm_ln_launch(w.resid, D, lw.ln1_g, lw.ln1_b, s.eps, tf ? w.resid : nullptr, lw.wqkv, D, lw.bqkv, w.qkv,
+                                              3 * a, M, 3 * a, D, EVT_ACT_NONE, st));
+    } else {
+      if (!xn_ready)
+        EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln1_g, lw.ln1_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+      EVT_STAGE(EVT_STAGE_QKV, gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
+                          EVT_ACT_NONE, st));
+    }
     xn_ready = false;
-    EVT_STAGE(EVT_STAGE_QKV, gemm_launch(w.xn, D, lw.wqkv, D, dt, lw.bqkv, nullptr, 0, 0, 0, w.qkv, adt, 3 * a, 0, 0, 0, M, 3 * a, D,
-                        EVT_ACT_NONE, st));
     // head mask row of this layer (are_16_heads mask_heads) and, on request, the context written straight into the caller's
     // buffer (context_layer_val): the output projection then reads its A operand from there
     const float* hmask = o.head_mask != nullptr ? o.head_mask + static_cast<size_t>(l) * o.head_mask_ld : nullptr;
@@ -465,10 +474,15 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
     {
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
                           EVT_ACT_NONE, st));
-      EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
+      if (!ln_in_gemm)
+        EVT_STAGE(EVT_STAGE_LN, layernorm_launch(w.resid, D, lw.ln2_g, lw.ln2_b, w.xn, adt, D, tf ? w.resid : nullptr, M, D, s.eps, st));
     }
-    EVT_STAGE(EVT_STAGE_FC1, gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
-                        st));
+    if (ln_in_gemm)
+      EVT_STAGE(EVT_STAGE_FC1, gemm_ln_launch(w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, tf ? w.resid : nullptr, lw.w1, D, lw.b1, w.big,
+                                              lw.inter_ld, M, lw.inter, D, s.act, st));
+    else
+      EVT_STAGE(EVT_STAGE_FC1, gemm_launch(w.xn, D, lw.w1, D, dt, lw.b1, nullptr, 0, 0, 0, w.big, adt, lw.inter_ld, 0, 0, 0, M, lw.inter, D, s.act,
+                          st));
 #ifdef EVT_EXPERIMENTAL
     if (fuse_ln && l + 1 < s.layers) {
       const LayerW& nx = m->layers[l + 1];

@@ -15,6 +15,11 @@ int gemm_res_ln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, c
                        const float* gamma, const float* beta, float eps, void* xn, int64_t ldxn, int64_t M, int N, int K,
                        cudaStream_t stream);
 
+// LayerNorm fused into the A-operand producer of the following projection (gemm_ln.cu); K = D in {64,128,192,256,384}
+bool gemm_ln_supported(int64_t M, int N, int K);
+int gemm_ln_launch(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* x_copy, const void* W,
+                   int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t M, int N, int K, int act, cudaStream_t stream);
+
 int attention_launch(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, const float* head_mask, int B, int S,
                      int heads, int head_size, float scale, cudaStream_t stream);
 

@@ -123,6 +123,29 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+def layernorm_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor,
+                     bias: Optional[torch.Tensor] = None, act=None, write_back: bool = False,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(LayerNorm(x) @ w^T + bias) in ONE kernel (the LayerNorm is the producer of the GEMM's A operand): x f32 [M, K]
+    with K in {64, 128, 192, 256, 384}, w bf16 [N, >=K] -> bf16 [M, N].  write_back: x <- LayerNorm(x) (TF dialect)."""
+    _need_cuda(x, gamma, beta, w, bias, out)
+    if x.dtype != torch.float32 or w.dtype != torch.bfloat16 or x.dim() != 2 or w.dim() != 2 or x.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("layernorm_linear wants a 2-D f32 x and a 2-D bf16 w with unit inner strides")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] < K:
+        raise ValueError("layernorm_linear: w has fewer columns than x")
+    if out is None:
+        ld = (N + 7) // 8 * 8
+        out = torch.empty((M, ld), dtype=torch.bfloat16, device=x.device)[:, :N]
+    lib = _lib.load()
+    rc = lib.evt_layernorm_gemm(x.data_ptr(), x.stride(0), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(), float(eps),
+                                x.data_ptr() if write_back else None, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
+                                out.stride(0), M, N, K, ACTS[act], _stream())
+    _lib.check(rc, "layernorm_gemm")
+    return out
+
+
 def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor,
                               gamma: torch.Tensor, beta: torch.Tensor, eps: float, k: Optional[int] = None,
                               xn: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -114,6 +114,18 @@ int evt_gemm_bias_act_tf32(const float* A, int64_t lda, const float* W, int64_t 
                            float* out, int64_t ldo, int out_group, int out_group_stride, int out_group_off,
                            int64_t M, int N, int K, int act, evt_stream stream);
 
+/* out[M,N] (bf16) = act( LayerNorm(x)[M,K] W[N,K]^T + bias ) -- the LayerNorm that precedes a projection, run inside
+ * the GEMM as the producer of its A operand: layernorm_before -> query|key|value and layernorm_after ->
+ * intermediate.dense of a ViT layer (SITE/models/vit/modeling_vit.py:333-340) for narrow residual streams, where the
+ * stand-alone LayerNorm pass is HBM traffic the encoder cannot afford (DeiT-Tiny / -Small, T2T-ViT).
+ *   x : f32 [M, ldx] (ldx % 4 == 0, 16-byte aligned); K = row length, one of 64, 128, 192, 256, 384
+ *   x_copy_f32 (nullable, may alias x): the normalised rows written back as f32 (TF dialect skip connection)
+ *   W : bf16 [N, ldw]; bias f32 [N] or NULL; out bf16 [M, ldo] (ldo % 8 == 0)
+ * Statistics are f32 with a centred variance, exactly as evt_layernorm_fwd computes them. */
+int evt_layernorm_gemm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* x_copy_f32,
+                       const void* W, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t M, int N, int K,
+                       int act, evt_stream stream);
+
 /* Residual projection with the following LayerNorm fused into the epilogue (bf16 A and W):
  *     resid[M,N] <- resid + A[M,K] W[N,K]^T + bias        (f32, in place)
  *     xn[M,N]    <- LayerNorm(resid) * gamma + beta        (bf16)

@@ -173,6 +173,37 @@ def test_gemm_residual_layernorm_fused(M, N, K):
     assert (xn.float() - want_xn).abs().max().item() < 4e-2
 
 
+@pytest.mark.parametrize("M,N,K,act", [(128 * 3 + 5, 576, 192, None), (1000, 230, 192, "gelu_erf"), (777, 1152, 384, None),
+                                       (300, 1536, 384, "gelu_erf"), (130, 192, 64, "gelu_tanh"), (515, 768, 256, "gelu_tanh"),
+                                       (128 * 150 + 77, 192, 192, None), (64, 100, 128, None)])
+def test_layernorm_fused_into_the_projection(M, N, K, act):
+    """evt_layernorm_gemm: act(LN(x) W^T + b) in one kernel against fp32 torch, and against the two-kernel path (LayerNorm
+    kernel + GEMM) -- same f32 statistics, same bf16 rounding of the normalised rows, so the outputs agree to bf16
+    rounding of the result.  Also the TF-dialect write-back of the normalised rows."""
+    ops = _ops()
+    x = _rand((M, K), 41) * 2 + 0.3 * _rand((M, 1), 42)
+    gamma = 1 + _rand((K,), 43, 0.1)
+    beta = _rand((K,), 44, 0.1)
+    w = _rand((N, K), 45, 0.05).bfloat16()
+    bias = _rand((N,), 46, 0.1)
+    eps = 1e-12 if K != 256 else 1e-5
+    xn_ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, eps)
+    z = xn_ref.bfloat16().float() @ w.float().t() + bias
+    ref = z if act is None else (ovit.gelu_erf(z) if act == "gelu_erf" else ovit.gelu_tanh(z))
+    got = ops.layernorm_linear(x, gamma, beta, eps, w, bias, act=act)
+    assert got.shape == (M, N) and got.dtype == torch.bfloat16
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    assert (got.float() - ref).abs().max().item() < tol
+    xn = ops.layernorm(x, gamma, beta, eps)
+    two = ops.linear(xn, w, bias, act=act)
+    assert (got.float() - two.float()).abs().max().item() <= 1.6e-2 * max(1.0, ref.abs().max().item())
+    assert (got.float() - two.float()).abs().mean().item() < 1e-4
+    x2 = x.clone()
+    got2 = ops.layernorm_linear(x2, gamma, beta, eps, w, bias, act=act, write_back=True)
+    assert torch.equal(got2, got)
+    assert (x2 - xn_ref).abs().max().item() < 2e-5 * max(1.0, xn_ref.abs().max().item())
+
+
 def test_gemm_residual_layernorm_constant_rows():
     """eps = 1e-12 and rows that are exactly constant: the centred variance must be exactly 0 -> xn == beta."""
     ops = _ops()
