@@ -52,12 +52,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread may sleep in hardware up to that long before the instruction returns
+// false; it is woken as soon as the phase completes.  Used by the retry loop below so that a waiting role re-issues a
+// handful of instructions per microsecond instead of spinning (the default time limit is ~100 cycles: the round-2
+// attention profile showed 21 retries per wait, 15 % of all issued instructions, competing with the other softmax group
+// for the sub-partition's issue slots).
+#ifndef EVT_MBAR_SUSPEND_NS
+#define EVT_MBAR_SUSPEND_NS 2000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(EVT_MBAR_SUSPEND_NS))
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
 // GPU that hangs until the box is killed.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
       printf("evt: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
