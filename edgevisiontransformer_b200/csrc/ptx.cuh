@@ -78,8 +78,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-      printf("evt: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
+      printf("evt: mbarrier wait timed out (block %d,%d,%d thread %d parity %u barrier @smem 0x%x)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity, smem_u32(bar));
       __trap();
     }
   }

@@ -1,4 +1,4 @@
-"""ncu target: every hot kernel of one DeiT-Base encoder layer at per-GPU batch 512, a few launches each
+"""ncu target: every hot kernel of one DeiT encoder layer (default Base; `B D heads inter` for another size), a few launches each
 (no timing here -- numbers printed under a profiler are never bench values)."""
 import os
 import sys
@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from edgevisiontransformer_b200 import ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-D, H, I, S = 768, 12, 3072, 197
+D, H, I = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (768, 12, 3072)   # e.g. 256 384 6 1536 = DeiT-Small
+S = 197
 M = B * S
 x = torch.randn(M, D, device="cuda")
 g, b0 = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
