@@ -34,6 +34,16 @@ __global__ void __launch_bounds__(256) convert_pad_kernel(const float* __restric
   store_as(dst + t, c < cols ? src[r * cols + c] : 0.f);
 }
 
+// dst[n, k] (bf16, leading dimension ld, zero padded) = src[k, n]: a Keras Dense kernel [in, out] as the [out, in] weight
+__global__ void __launch_bounds__(256) convert_pad_transposed_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                     int rows_out, int cols_out, int ld) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(rows_out) * ld) return;
+  const int c = static_cast<int>(t % ld);
+  const int r = static_cast<int>(t / ld);
+  dst[t] = __float2bfloat16_rn(c < cols_out ? src[static_cast<long long>(c) * rows_out + r] : 0.f);
+}
+
 // bf16 rows gathered with a stride from an f32 matrix (cls rows for a head without final LN)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_cast_kernel(const float* __restrict__ x, long long x_stride,
@@ -57,6 +67,14 @@ struct LayerW {
   int a = 0, inter = 0, inter_ld = 0;
 };
 
+// one TokenPerformer of the T2T front-end (modeling/layers/transformer_encoder.py:39-101), emb = 64, m = 32
+struct PerformerW {
+  int in_dim = 0, in_ld = 0;            // 147 / 576, leading dimension of the unfolded rows (multiple of 8)
+  float *g1 = nullptr, *b1 = nullptr;   // norm1 over the unfolded row
+  __nv_bfloat16 *wkqv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bkqv = nullptr, *w = nullptr, *bo = nullptr, *g2 = nullptr, *b2 = nullptr, *bb1 = nullptr, *bb2 = nullptr;
+};
+
 }  // namespace
 }  // namespace evt
 
@@ -77,6 +95,7 @@ struct evt_model {
   float* b_pre = nullptr;
   uint8_t* w_cls = nullptr;
   float* b_cls = nullptr;
+  evt::PerformerW perf[2];   // spec.t2t: the two TokenPerformers of the tokens-to-token module
   std::vector<void*> allocs;
   // evt_model_profile_begin/end: one event before the first launch and one after every launch of a forward
   bool profiling = false;
@@ -91,8 +110,19 @@ namespace {
 struct Workspace {
   float* resid;
   uint8_t *xn, *qkv, *ctx, *big, *clsn, *hh;  // activations in the GEMM operand type (bf16, or f32 in tf32 mode)
+  // T2T front-end (spec.t2t): per performer stage the unfolded + normalised rows, k|q|v, the attention output, the f32
+  // token stream y, LN(y), the MLP hidden rows and the performer scratch; `pm` = the patch matrix of the embedding GEMM
+  uint8_t *t_x[2], *t_kqv[2], *t_ya[2], *t_z[2], *t_h[2], *t_ws[2], *t_pm;
+  float* t_y[2];
   size_t bytes;
 };
+
+// token grid of the T2T soft splits for a square image: unfold(7,4,2) -> unfold(3,2,1) -> unfold(3,2,1)
+inline int t2t_side(int image, int stage) {
+  int s = (image + 2 * 2 - 7) / 4 + 1;
+  for (int i = 0; i < stage; ++i) s = (s + 2 * 1 - 3) / 2 + 1;
+  return s;
+}
 
 Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   const evt_model_spec& s = m->spec;
@@ -120,6 +150,18 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   const size_t o_big = take(std::max(M * imax_ld, (s.embed_k > 0 ? Mp : M) * static_cast<size_t>(m->patch_k)) * es);
   const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * es);
   const size_t o_hh = take(static_cast<size_t>(batch) * std::max(padn(s.head_hidden, m->pad), 8) * es);
+  if (s.t2t) {
+    for (int i = 0; i < 2; ++i) {
+      const size_t T = static_cast<size_t>(t2t_side(s.image, i)) * t2t_side(s.image, i) * batch;
+      const size_t in_ld = i == 0 ? 152 : 576;
+      const size_t ox = take(T * in_ld * 2), ok = take(T * 192 * 2), oa = take(T * 64 * 2), oy = take(T * 64 * 4);
+      const size_t oz = take(T * 64 * 2), oh = take(T * 64 * 2);
+      const size_t ow = take(performer_workspace_bytes(batch, t2t_side(s.image, i) * t2t_side(s.image, i)));
+      w.t_x[i] = b + ox, w.t_kqv[i] = b + ok, w.t_ya[i] = b + oa, w.t_y[i] = reinterpret_cast<float*>(b + oy);
+      w.t_z[i] = b + oz, w.t_h[i] = b + oh, w.t_ws[i] = b + ow;
+    }
+    w.t_pm = b + take(Mp * 576 * 2);
+  }
   w.resid = reinterpret_cast<float*>(b + o_resid);
   w.xn = b + o_xn;
   w.qkv = b + o_qkv;
@@ -148,6 +190,10 @@ int validate_spec(const evt_model_spec* s) {
   EVT_CHECK_ARG(s->head_hidden >= 0, "head_hidden must be >= 0");
   EVT_CHECK_ARG(s->precision == EVT_PREC_BF16 || s->precision == EVT_PREC_TF32, "precision must be bf16 (0) or tf32 (1)");
   EVT_CHECK_ARG(s->embed_k >= 0 && s->embed_k % 8 == 0, "embed_k must be a non-negative multiple of 8");
+  if (s->t2t) {
+    EVT_CHECK_ARG(s->embed_k == 576 && s->precision == EVT_PREC_BF16, "the T2T front-end needs embed_k = 576 (3 x 3 x 64) and the bf16 mode");
+    EVT_CHECK_ARG(t2t_side(s->image, 2) * t2t_side(s->image, 2) == patches, "image size does not give image/16 squared T2T tokens");
+  }
   for (int l = 0; l < s->layers; ++l) {
     EVT_CHECK_ARG(s->heads[l] > 0, "every layer must keep at least one head");
     EVT_CHECK_ARG(s->inter[l] > 0, "every layer must keep at least one FFN unit");
@@ -214,6 +260,22 @@ struct Loader {
     else convert_pad_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), rows, cols, ld);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(EVT_ERR_CUDA, std::string("convert_pad: ") + cudaGetErrorString(e));
+    return EVT_OK;
+  }
+  // bf16 [rows_out, ld] from an f32 Keras kernel [cols_out, rows_out]
+  int mat_t(const std::string& name, int rows_out, int cols_out, int ld, __nv_bfloat16** out) {
+    const evt_tensor_view* v;
+    int rc = need(name, static_cast<int64_t>(rows_out) * cols_out, &v);
+    if (rc) return rc;
+    void* p;
+    rc = alloc(static_cast<size_t>(rows_out) * ld * 2, &p);
+    if (rc) return rc;
+    *out = reinterpret_cast<__nv_bfloat16*>(p);
+    const long long total = static_cast<long long>(rows_out) * ld;
+    convert_pad_transposed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(v->data), *out,
+                                                                                               rows_out, cols_out, ld);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EVT_ERR_CUDA, std::string("convert_pad_transposed: ") + cudaGetErrorString(e));
     return EVT_OK;
   }
   int mat(const std::string& name, int64_t rows, int cols, int ld, uint8_t** out) {
@@ -326,6 +388,27 @@ extern "C" int evt_model_load_weights(evt_model* m, const evt_tensor_view* tenso
     EVT_TRY(L.vec(p + "layernorm_after.weight", D, false, &w.ln2_g));
     EVT_TRY(L.vec(p + "layernorm_after.bias", D, false, &w.ln2_b));
   }
+  if (s.t2t) {  // Keras variable names of T2T_module (modeling/models/t2t_vit.py:47-59), Dense kernels [in, out]
+    for (int i = 0; i < 2; ++i) {
+      PerformerW& pw = m->perf[i];
+      const std::string p = "t2t.performer" + std::to_string(i + 1) + ".";
+      pw.in_dim = i == 0 ? 7 * 7 * 3 : 3 * 3 * 64;
+      pw.in_ld = padn(pw.in_dim, 8);
+      EVT_TRY(L.vec(p + "norm1.gamma", pw.in_dim, false, &pw.g1));
+      EVT_TRY(L.vec(p + "norm1.beta", pw.in_dim, false, &pw.b1));
+      EVT_TRY(L.mat_t(p + "kqv.kernel", 192, pw.in_dim, pw.in_ld, &pw.wkqv));
+      EVT_TRY(L.vec(p + "kqv.bias", 192, true, &pw.bkqv));
+      EVT_TRY(L.vec(p + "w", 32 * 64, false, &pw.w));
+      EVT_TRY(L.mat_t(p + "attn_output.kernel", 64, 64, 64, &pw.wo));
+      EVT_TRY(L.vec(p + "attn_output.bias", 64, true, &pw.bo));
+      EVT_TRY(L.vec(p + "norm2.gamma", 64, false, &pw.g2));
+      EVT_TRY(L.vec(p + "norm2.beta", 64, false, &pw.b2));
+      EVT_TRY(L.mat_t(p + "mlp.fc1.kernel", 64, 64, 64, &pw.w1));
+      EVT_TRY(L.vec(p + "mlp.fc1.bias", 64, true, &pw.bb1));
+      EVT_TRY(L.mat_t(p + "mlp.fc2.kernel", 64, 64, 64, &pw.w2));
+      EVT_TRY(L.vec(p + "mlp.fc2.bias", 64, true, &pw.bb2));
+    }
+  }
   if (s.final_ln) {
     EVT_TRY(L.vec("vit.layernorm.weight", D, false, &m->lnf_g));
     EVT_TRY(L.vec("vit.layernorm.bias", D, false, &m->lnf_b));
@@ -354,7 +437,8 @@ extern "C" int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* 
 extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   if (!m) return 0;
   const evt_model_spec& s = m->spec;
-  return (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+  // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels, attn_output, LN, fc1, fc2; then the last soft split
+  return (s.t2t ? 2 * 9 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
 static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts* opts, const void* patch_matrix, int64_t patch_ld,
@@ -406,6 +490,37 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
   const bool tf32 = s.precision == EVT_PREC_TF32;
   const int dt = tf32 ? EVT_F32 : EVT_BF16;   // GEMM operand type
   const int adt = tf32 ? EVT_TF32 : EVT_BF16;  // type activations are WRITTEN in (tf32: f32 storage, rounded to nearest)
+  // tokens-to-token front-end (T2T_module.call, modeling/models/t2t_vit.py:63-88): pixels are NHWC f32 here
+  if (s.t2t && patch_matrix == nullptr) {
+    const float tf_eps = 1e-5f;   // tf.keras.layers.LayerNormalization(epsilon=1e-5), transformer_encoder.py:49-50
+    const void* src = pixels;
+    int src_dt = EVT_F32, side = s.image, ch = 3;
+    EVT_CHECK_ARG(o.pixel_dtype == EVT_PIX_F32, "the T2T front-end takes f32 NHWC pixels");
+    for (int i = 0; i < 2; ++i) {
+      const PerformerW& pw = m->perf[i];
+      const int k = i == 0 ? 7 : 3, st_ = i == 0 ? 4 : 2, pad_ = i == 0 ? 2 : 1;
+      const int so = t2t_side(s.image, i), T = so * so;
+      const int64_t rows = static_cast<int64_t>(batch) * T;
+      EVT_STAGE(EVT_STAGE_EMBED, unfold_ln_launch(src, src_dt, w.t_x[i], pw.in_ld, pw.g1, pw.b1, tf_eps, batch, side, side, ch, k, st_, pad_, st));
+      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_x[i], pw.in_ld, pw.wkqv, pw.in_ld, EVT_BF16, pw.bkqv, nullptr, 0, 0, 0, w.t_kqv[i], EVT_BF16, 192,
+                                             0, 0, 0, rows, 192, pw.in_dim, EVT_ACT_NONE, st));
+      EVT_TRY(performer_launch(w.t_kqv[i], 192, pw.w, w.t_ya[i], w.t_y[i], w.t_ws[i], batch, T, 64, 32, 1e-8f, st));
+      EVT_TRY(mark(EVT_STAGE_EMBED));
+      // y = v + attn_output(.)   (transformer_encoder.py:93)
+      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_ya[i], 64, pw.wo, 64, EVT_BF16, pw.bo, w.t_y[i], 64, 0, 0, w.t_y[i], EVT_F32, 64, 0, 0, 0, rows,
+                                             64, 64, EVT_ACT_NONE, st));
+      EVT_STAGE(EVT_STAGE_EMBED, layernorm_launch(w.t_y[i], 64, pw.g2, pw.b2, w.t_z[i], EVT_BF16, 64, nullptr, rows, 64, tf_eps, st));
+      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_z[i], 64, pw.w1, 64, EVT_BF16, pw.bb1, nullptr, 0, 0, 0, w.t_h[i], EVT_BF16, 64, 0, 0, 0, rows, 64,
+                                             64, EVT_ACT_GELU_TANH, st));
+      // y += mlp(LN(y))   (:99)
+      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_h[i], 64, pw.w2, 64, EVT_BF16, pw.bb2, w.t_y[i], 64, 0, 0, w.t_y[i], EVT_F32, 64, 0, 0, 0, rows,
+                                             64, 64, EVT_ACT_NONE, st));
+      src = w.t_y[i], src_dt = EVT_F32, side = so, ch = 64;
+    }
+    EVT_STAGE(EVT_STAGE_EMBED, unfold_ln_launch(src, src_dt, w.t_pm, 576, nullptr, nullptr, tf_eps, batch, side, side, 64, 3, 2, 1, st));
+    patch_matrix = w.t_pm;
+    patch_ld = 576;
+  }
   // embeddings
   if (patch_matrix == nullptr) {
     // Pixels path: the patch matrix gets one row per token (prefix rows zero), so the embedding GEMM is a plain

@@ -39,6 +39,12 @@ int im2col4_launch(const float* pixels, void* cols, int B, int H, int W, int P, 
 int prefix_tokens_launch(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix, int D,
                          cudaStream_t st);
 int cast_launch(const float* x, void* y, int64_t n, cudaStream_t st);
+// T2T front-end pieces (performer.cu)
+int unfold_ln_launch(const void* x, int x_dtype, void* out, int64_t ldo, const float* gamma, const float* beta, float eps, int B,
+                     int H, int W, int C, int k, int s, int p, cudaStream_t st);
+size_t performer_workspace_bytes(int B, int T);
+int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace, int B, int T, int emb,
+                     int m, float eps, cudaStream_t st);
 int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k, int s, int p,
                   cudaStream_t st);
 

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ops.h"
 #include "ptx.cuh"
 
 namespace evt {
@@ -519,8 +520,7 @@ extern "C" int evt_unfold_ln_nhwc(const void* x, int x_dtype, void* out, int64_t
 
 extern "C" int evt_performer_workspace_bytes(int B, int T, size_t* out) {
   EVT_CHECK_ARG(out != nullptr && B > 0 && T > 0, "performer_workspace_bytes: bad arguments");
-  const size_t nsplit = (T + kChunk - 1) / kChunk;
-  *out = static_cast<size_t>(B) * (nsplit + 1) * (kM + kEmb * kM) * sizeof(float);
+  *out = evt::performer_workspace_bytes(B, T);
   return EVT_OK;
 }
 
@@ -528,6 +528,18 @@ extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, vo
                                  int B, int T, int emb, int m, float eps, evt_stream stream) {
   int rc = evt_device_check();
   if (rc != EVT_OK) return rc;
+  return evt::performer_launch(kqv, ld, w, yattn, vout, workspace, B, T, emb, m, eps, static_cast<cudaStream_t>(stream));
+}
+
+namespace evt {
+
+size_t performer_workspace_bytes(int B, int T) {
+  const size_t nsplit = (T + kChunk - 1) / kChunk;
+  return static_cast<size_t>(B) * (nsplit + 1) * (kM + kEmb * kM) * sizeof(float);
+}
+
+int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace, int B, int T, int emb,
+                     int m, float eps, cudaStream_t st) {
   EVT_CHECK_ARG(kqv && w && yattn && vout && workspace, "performer: null pointer");
   EVT_CHECK_ARG(B > 0 && T > 0 && B <= 65535, "performer: B in 1..65535 and T > 0");
   if (emb != kEmb || m != kM) return fail(EVT_ERR_UNSUPPORTED, "performer: only emb = 64, m = 32 (T2T token_size 64, kernel_ratio 0.5) is implemented");
@@ -536,7 +548,6 @@ extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, vo
   EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(w) % 8 == 0 && reinterpret_cast<uintptr_t>(workspace) % 8 == 0 &&
                     reinterpret_cast<uintptr_t>(yattn) % 4 == 0 && reinterpret_cast<uintptr_t>(vout) % 8 == 0,
                 "performer: w / workspace / outputs must be 8-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nsplit = (T + kChunk - 1) / kChunk;
   float* partial = reinterpret_cast<float*>(workspace);
   float* stats = partial + static_cast<size_t>(B) * nsplit * (kM + kEmb * kM);
@@ -550,3 +561,5 @@ extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, vo
   EVT_LAUNCH_CHECK("performer_apply");
   return EVT_OK;
 }
+
+}  // namespace evt

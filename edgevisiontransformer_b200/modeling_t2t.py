@@ -90,9 +90,15 @@ class B200T2TViT(nn.Module):
         c["vit.layernorm.weight"], c["vit.layernorm.bias"] = sd["norm.gamma"], sd["norm.beta"]
         c["classifier.weight"] = sd["classifier_head.kernel"].t().contiguous()
         c["classifier.bias"] = sd["classifier_head.bias"]
+        # The tokens-to-token module runs inside the library too (evt_model_forward with spec.t2t = 1: soft splits, the two
+        # TokenPerformers and the project GEMM are part of the C++ launch sequence); its Keras variables go in under their own
+        # names.  `tokens()` below keeps an op-level composition of the same module for tests that look at the tokens.
+        for k, v in sd.items():
+            if k.startswith("t2t.performer"):
+                c[k] = v
         self.core = B200ViTForImageClassification.from_state_dict(
             c, device=dev, max_batch=max_batch, dialect="tf", hidden_act="gelu_tanh", layer_norm_eps=TF_EPS, final_ln=True,
-            head_size=D // num_heads, embed_k=sd["t2t.project.kernel"].shape[0], precision=precision)
+            head_size=D // num_heads, embed_k=sd["t2t.project.kernel"].shape[0], precision=precision, t2t=True)
         self.config = self.core.config
         self._graphs: dict = {}
         # The graphs captured by forward_graphed bake in the core's activation workspace pointer: drop them whenever the core
@@ -115,12 +121,18 @@ class B200T2TViT(nn.Module):
         if x.dim() != 4 or x.shape[-1] != 3:
             raise ValueError("T2T-ViT takes channel-last images [B, H, W, 3] (t2t_vit.py:65)")
         x = x.float().contiguous()
-        outs = []
+        return ImageClassifierOutput(logits=self._forward_core(x))
+
+    def _forward_core(self, x: torch.Tensor) -> torch.Tensor:
+        """One C call per chunk: front-end + encoder + head (evt_model_forward on NHWC f32 pixels)."""
+        c = self.config
+        if x.shape[1] != c.image_size or x.shape[2] != c.image_size:
+            raise ValueError(f"Input image size ({tuple(x.shape[1:3])}) doesn't match model ({c.image_size}*{c.image_size}).")
+        logits = torch.empty((x.shape[0], c.num_labels), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self._dev):
             for s in range(0, x.shape[0], self.max_batch):
-                pm = self.tokens(x[s:s + self.max_batch])
-                outs.append(self.core.forward_embedded(pm).logits)
-        return ImageClassifierOutput(logits=torch.cat(outs) if len(outs) > 1 else outs[0])
+                self.core._run(x[s:s + self.max_batch], logits[s:s + self.max_batch])
+        return logits
 
     @torch.no_grad()
     def forward_graphed(self, x: torch.Tensor) -> ImageClassifierOutput:
@@ -130,11 +142,10 @@ class B200T2TViT(nn.Module):
         if x.shape[0] > self.max_batch:
             return self.forward(x)
         from .graph_util import graphed_call
-        return ImageClassifierOutput(logits=graphed_call(
-            self._graphs, x, lambda xin: self.core.forward_embedded(self.tokens(xin)).logits, self._dev))
+        return ImageClassifierOutput(logits=graphed_call(self._graphs, x.float(), self._forward_core, self._dev))
 
     def launches_per_forward(self) -> int:
-        return 2 * 9 + 1 + self.core.launches_per_forward() - 1
+        return self.core.launches_per_forward()
 
 
 def get_t2t_vit_14(sd, **kw):

@@ -40,6 +40,7 @@ class B200ViTConfig:
     head_hidden: int = 0
     precision: str = "bf16"           # "bf16" (2e-2 logit tolerance) | "tf32" (1e-3; f32 activations)
     embed_k: int = 0                  # >0: caller-built patch matrix with this K (T2T: 576), see forward_embedded
+    t2t: bool = False                 # tokens-to-token front-end inside the library (NHWC f32 pixels; needs embed_k = 576)
 
     # names the reference's callers read off model.config
     @property
@@ -71,7 +72,7 @@ _PIX = {torch.float32: _lib.PIX_F32, torch.bfloat16: _lib.PIX_BF16, torch.uint8:
 
 def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12, hidden_act="gelu", head_size=64,
                            image_size=224, patch_size=16, dialect="hf", final_ln=None, head_hidden=None,
-                           precision="bf16", embed_k=0) -> B200ViTConfig:
+                           precision="bf16", embed_k=0, t2t=False) -> B200ViTConfig:
     D = sd["vit.embeddings.cls_token"].shape[-1]
     L = 0
     while f"vit.encoder.layer.{L}.attention.attention.query.weight" in sd:
@@ -93,7 +94,7 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12,
                          tokens=sd["vit.embeddings.position_embeddings"].shape[-2], image_size=image_size,
                          patch_size=patch_size, num_labels=sd["classifier.weight"].shape[0],
                          layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, dialect=dialect, final_ln=bool(final_ln),
-                         head_hidden=int(head_hidden), precision=precision, embed_k=int(embed_k))
+                         head_hidden=int(head_hidden), precision=precision, embed_k=int(embed_k), t2t=bool(t2t))
 
 
 class B200ViTForImageClassification(nn.Module):
@@ -143,7 +144,7 @@ class B200ViTForImageClassification(nn.Module):
             spec.inter[l] = int(config.intermediate[l])
         spec.final_ln = int(config.final_ln)
         spec.head_hidden = int(config.head_hidden)
-        spec.t2t = 0
+        spec.t2t = int(bool(config.t2t))
         spec.embed_k = int(config.embed_k)
         if config.precision not in ("bf16", "tf32"):
             raise ValueError(f"unsupported precision {config.precision!r}")
@@ -180,7 +181,7 @@ class B200ViTForImageClassification(nn.Module):
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], config: Optional[B200ViTConfig] = None, **kw):
         sd = normalise_keys(sd)
         cfg_kw = {k: kw.pop(k) for k in list(kw) if k in ("layer_norm_eps", "hidden_act", "head_size", "image_size",
-                                                            "patch_size", "dialect", "final_ln", "head_hidden", "precision", "embed_k")}
+                                                            "patch_size", "dialect", "final_ln", "head_hidden", "precision", "embed_k", "t2t")}
         config = config or config_from_state_dict(sd, **cfg_kw)
         return cls(config, sd, **kw)
 

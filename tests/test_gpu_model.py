@@ -170,6 +170,13 @@ def test_t2t_front_end_and_model():
     assert err < 5e-2, err
     r = ovit.compare_logits(m(x.cuda()).logits, want_logits)
     assert r["max_abs"] <= BF16_TOL and r["top1_agree"] == 1.0, r
+    # the front-end inside the C++ runtime (evt_model_forward, spec.t2t) issues the same kernels as the op-level composition
+    try:
+        ops.set_gemm_split_k(False)
+        assert torch.equal(m(x.cuda()).logits, m.core.forward_embedded(m.tokens(x.cuda())).logits)
+    finally:
+        ops.set_gemm_split_k(True)
+    assert m.launches_per_forward() == 19 + 2 + 7 * 3 + 2
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 224, 224, device="cuda"))
     for _ in range(2):                                   # latency path: one CUDA graph over front-end + encoder
