@@ -41,6 +41,15 @@ class ForwardOpts(C.Structure):
 PIX_F32, PIX_BF16, PIX_U8 = 0, 1, 2
 
 
+SWIN_MAX_STAGES = 8
+
+
+class SwinSpec(C.Structure):
+    _fields_ = [("image", C.c_int), ("patch", C.c_int), ("window", C.c_int), ("embed_dim", C.c_int), ("stages", C.c_int),
+                ("depths", C.c_int * SWIN_MAX_STAGES), ("heads", C.c_int * SWIN_MAX_STAGES), ("num_labels", C.c_int),
+                ("eps", C.c_float)]
+
+
 class TensorView(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4)]
 
@@ -85,6 +94,12 @@ SIGNATURES = {
     "evt_model_profile_begin": (_i, [_p]),
     "evt_model_profile_end": (_i, [_p, C.POINTER(_f), C.POINTER(_i)]),
     "evt_model_destroy": (_i, [_p]),
+    "evt_swin_create": (_i, [C.POINTER(SwinSpec), C.POINTER(_p)]),
+    "evt_swin_load_weights": (_i, [_p, C.POINTER(TensorView), _i, _p]),
+    "evt_swin_workspace_bytes": (_i, [_p, _i, C.POINTER(_sz)]),
+    "evt_swin_forward": (_i, [_p, _p, _i, _p, _p, _sz, _p]),
+    "evt_swin_launches_per_forward": (_i, [_p]),
+    "evt_swin_destroy": (_i, [_p]),
 }
 
 _lib = None

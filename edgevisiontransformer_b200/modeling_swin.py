@@ -20,7 +20,9 @@ from typing import Dict, List, Sequence
 import torch
 import torch.nn as nn
 
-from . import ops
+import ctypes as ct
+
+from . import _lib, ops
 from .modeling_vit import ImageClassifierOutput
 
 LOG2E = 1.4426950408889634
@@ -158,6 +160,31 @@ class B200SwinForImageClassification(nn.Module):
         self.num_labels = self.w_cls.shape[0]
         self.config = B200SwinConfig(depths, num_heads, embed_dim, window, patch, image_size, eps, self.num_labels)
         self._param = nn.Parameter(self.b_cls, requires_grad=False)       # next(model.parameters()).device works
+        # The C++ runtime (evt_swin_*, csrc/swin_model.cu): same weights under their HF names, the window orders / gathers /
+        # bias + mask tables recomputed on the host inside the library; one call issues the whole launch sequence.  The
+        # op-level composition above (_run_ops) stays as the cross-check of the tests.
+        self._lib = _lib.load()
+        self._handle = ct.c_void_p()
+        self._ws, self._ws_batch = None, 0
+        spec = _lib.SwinSpec()
+        spec.image, spec.patch, spec.window, spec.embed_dim = image_size, patch, window, embed_dim
+        spec.stages, spec.num_labels, spec.eps = len(self.depths), self.num_labels, float(eps)
+        for i, (d, h) in enumerate(zip(self.depths, self.num_heads)):
+            spec.depths[i], spec.heads[i] = int(d), int(h)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.evt_swin_create(ct.byref(spec), ct.byref(self._handle)), "swin_create")
+            dev_sd = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sd.items()
+                      if torch.is_tensor(v) and v.is_floating_point()}
+            views = (_lib.TensorView * len(dev_sd))()
+            keep = []
+            for i, (k, v) in enumerate(dev_sd.items()):
+                name = k.encode()
+                keep.append(name)
+                views[i].name, views[i].data, views[i].ndim = name, v.data_ptr(), 1
+                views[i].shape[0] = v.numel()
+            _lib.check(self._lib.evt_swin_load_weights(self._handle, views, len(dev_sd), torch.cuda.current_stream().cuda_stream),
+                       "swin_load_weights")
+        self.use_ops = False        # True: the Python-composed op sequence instead of the C++ runtime (tests)
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -188,8 +215,38 @@ class B200SwinForImageClassification(nn.Module):
             raise RuntimeError("B200SwinForImageClassification is inference-only")
         return super().train(False)
 
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.evt_swin_destroy(self._handle)
+                self._handle = ct.c_void_p()
+        except Exception:
+            pass
+
+    def launches_per_forward(self) -> int:
+        return int(self._lib.evt_swin_launches_per_forward(self._handle))
+
     # ------------------------------------------------------------------ forward
+    def _workspace(self, batch: int) -> torch.Tensor:
+        if self._ws is None or batch > self._ws_batch:
+            n = ct.c_size_t()
+            _lib.check(self._lib.evt_swin_workspace_bytes(self._handle, batch, ct.byref(n)), "swin_workspace_bytes")
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=self._device)
+            self._ws_batch = batch
+            self._graphs.clear()       # captured graphs hold the old workspace pointer
+        return self._ws
+
     def _run(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_ops:
+            return self._run_ops(x)
+        B = x.shape[0]
+        ws = self._workspace(B)
+        logits = torch.empty((B, self.num_labels), dtype=torch.float32, device=x.device)
+        _lib.check(self._lib.evt_swin_forward(self._handle, x.data_ptr(), B, logits.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream), "swin_forward")
+        return logits
+
+    def _run_ops(self, x: torch.Tensor) -> torch.Tensor:
         with ops.static_weights():          # every linear() below multiplies by a weight matrix this module owns
             return self._run_impl(x)
 

@@ -314,6 +314,38 @@ int evt_model_profile_begin(evt_model* m);
 int evt_model_profile_end(evt_model* m, float* stage_ms /* [EVT_STAGE_COUNT] */, int* stage_launches /* [EVT_STAGE_COUNT] */);
 int evt_model_destroy(evt_model* m);
 
+/* ------------------------------------------------------------------ Swin model level ----- */
+
+/* The shifted-window classifier the reference builds with utils.get_swin (utils.py:14-47) and exports / benchmarks in
+ * tools.py:265-292 (swin_{tiny,small,base}_patch4_window7_224), arithmetic as in SITE/models/swin/modeling_swin.py.
+ * One call = the whole forward as a fixed launch sequence on `stream` (CUDA-graph capturable).  bf16 operands, f32
+ * accumulate / residual stream / LayerNorm / softmax. */
+typedef struct evt_swin evt_swin;
+
+#define EVT_SWIN_MAX_STAGES 8
+
+typedef struct evt_swin_spec {
+  int image, patch, window;          /* 224, 4, 7 */
+  int embed_dim;                     /* 96 (tiny / small), 128 (base); head size is 32 in every stage */
+  int stages;                        /* 4 */
+  int depths[EVT_SWIN_MAX_STAGES];   /* blocks per stage, e.g. 2, 2, 6, 2 */
+  int heads[EVT_SWIN_MAX_STAGES];    /* heads per stage, e.g. 3, 6, 12, 24 */
+  int num_labels;
+  float eps;                         /* LayerNorm epsilon (1e-5) */
+} evt_swin_spec;
+
+int evt_swin_create(const evt_swin_spec* spec, evt_swin** out);
+/* Weights under their HF names (swin.embeddings..., swin.encoder.layers.{s}.blocks.{b}..., swin.layernorm, classifier),
+ * f32 DEVICE tensors.  The window orders, cyclic-shift gathers, patch-merging gathers and the (relative position bias +
+ * shift mask) tables are computed here on the host from the geometry and the bias tables.  Allocates; synchronises. */
+int evt_swin_load_weights(evt_swin* m, const evt_tensor_view* tensors, int n, evt_stream stream);
+int evt_swin_workspace_bytes(const evt_swin* m, int batch, size_t* out);
+/* logits[batch, num_labels] (f32) = forward(pixels f32 NCHW [batch,3,image,image]) */
+int evt_swin_forward(evt_swin* m, const float* pixels, int batch, float* logits, void* workspace, size_t workspace_bytes,
+                     evt_stream stream);
+int evt_swin_launches_per_forward(const evt_swin* m);
+int evt_swin_destroy(evt_swin* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,23 @@ def test_swin_matches_oracle_and_golden(golden_dir, name, depths, seed, bs):
     r = ovit.compare_logits(m2(x[:1].cuda()).logits, want[:1])       # (not bit-equal run to run: split-K, include/evt.h)
     assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
     assert m.num_parameters() == sum(p.numel() for p in hf.parameters())
+    # the C++ runtime (evt_swin_forward: tables and gathers recomputed on the host inside the library) issues the same kernels
+    # on the same data as the op-level composition in modeling_swin.py
+    from edgevisiontransformer_b200 import ops
+    try:
+        ops.set_gemm_split_k(False)
+        a = m(pixel_values=x.cuda()).logits
+        m.use_ops = True
+        b = m(pixel_values=x.cuda()).logits
+        assert torch.equal(a, b)
+    finally:
+        m.use_ops = False
+        ops.set_gemm_split_k(True)
+    n_blocks = sum(hf.config.depths)
+    assert m.launches_per_forward() == 3 + 7 * n_blocks + 2 * (len(hf.config.depths) - 1) + 2
+    g = m.forward_graphed(x[:1].cuda()).logits
+    r = ovit.compare_logits(g, want[:1])
+    assert r["max_abs"] <= 2e-2 and r["top1_agree"] == 1.0, r
     with pytest.raises(RuntimeError):
         m(x)                                                           # CPU input: no fallback
     with pytest.raises(ValueError):
