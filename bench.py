@@ -419,19 +419,24 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         assert lg.shape == (per, 1000) and not lg.is_cuda
-        return gbatch / (float(tt.item()) / args.steps / 1e3)
+        step_s = float(tt.item()) / args.steps / 1e3
+        e2e_run.h2d_gbs = host.numel() * host.element_size() / step_s / 1e9     # per-GPU host -> device rate this implies
+        return gbatch / step_s
 
     host = torch.empty((per, 3, 224, 224), dtype=torch.float32).pin_memory()
     host.copy_(x)
     e2e_value = e2e_run(host)
+    e2e_h2d_gbs = e2e_run.h2d_gbs
     e2e_alt = {}
     hb = torch.empty((per, 3, 224, 224), dtype=torch.bfloat16).pin_memory()
     hb.copy_(x)
     del host
-    e2e_alt["bf16_pixels"] = {"value": e2e_run(hb), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 2}
+    e2e_alt["bf16_pixels"] = {"value": e2e_run(hb), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 2,
+                              "h2d_gb_per_s_per_gpu": e2e_run.h2d_gbs}
     del hb
     hu = torch.randint(0, 256, (per, 3, 224, 224), dtype=torch.uint8).pin_memory()
     e2e_alt["u8_pixels"] = {"value": e2e_run(hu), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224,
+                            "h2d_gb_per_s_per_gpu": e2e_run.h2d_gbs,
                             "note": "raw uint8 images, ImageNet mean/std normalisation fused into the patch gather"}
     del hu
 
@@ -524,7 +529,9 @@ def main():
                        "l2": "inputs larger than L2 (%.0f MB of pixels per step)" % (per * 3 * 224 * 224 * 4 / 1e6),
                        "preroll": "%d untimed steps over %.1f s before the timed region (sustained clocks)" % (pre_steps, args.preroll_s)},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 4,
-                    "d2h_bytes_per_step": per * 1000 * 4, "pixels": "f32 pinned host memory", "other_pixel_types": e2e_alt},
+                    "d2h_bytes_per_step": per * 1000 * 4, "pixels": "f32 pinned host memory",
+                    "h2d_gb_per_s_per_gpu": e2e_h2d_gbs, "ratio_to_device_resident": e2e_value / value,
+                    "other_pixel_types": e2e_alt},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
