@@ -72,6 +72,7 @@ SIGNATURES = {
     "evt_gemm_bias_act_tf32": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _p, _i64, _i, _i, _i, _i64, _i, _i, _i, _p]),
     "evt_layernorm_gemm": (_i, [_p, _i64, _p, _p, _f, _p, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p]),
     "evt_gemm_residual_layernorm": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _f, _p, _i64, _i64, _i, _i, _p]),
+    "evt_gemm_residual_layernorm_ex": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _f, _i, _p, _i64, _i64, _i, _i, _p]),
     "evt_attention_fwd": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _p]),
     "evt_attention_fwd_tf32": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _i, _f, _p]),
     "evt_im2col_patch": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libevt.so")
 OBJ_DIR = os.path.join(CSRC, "build")
 
-SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "gemm_ln.cu", "attention.cu", "layernorm.cu", "embed.cu", "performer.cu", "swin.cu", "swin_model.cu", "model.cu"]
+SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "gemm_ln.cu", "gemm_rowln.cu", "attention.cu", "layernorm.cu", "embed.cu", "performer.cu", "swin.cu", "swin_model.cu", "model.cu"]
 # Kernels that lost their A/B (kept as negative results): the GEMM + LayerNorm epilogue fusion (gemm3.cu) and the
 # single-group ping-pong attention variants.  EVT_EXPERIMENTAL=1 in the environment builds them into the library.
 EXPERIMENTAL = os.environ.get("EVT_EXPERIMENTAL", "0") not in ("", "0")

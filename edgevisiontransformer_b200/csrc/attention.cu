@@ -728,7 +728,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             o.z = *reinterpret_cast<uint32_t*>(&t2);
             o.w = *reinterpret_cast<uint32_t*>(&t3);
             const int piece = half * 4 + (jj >> 3);
-            *reinterpret_cast<uint4*>(stg_row + ((piece ^ sw) << 4)) = o;
+            ptx::sts_u4(ptx::smem_u32(stg_row) + ((piece ^ sw) << 4), o.x, o.y, o.z, o.w);  // explicit STS (a C++ store here is generic)
           }
         }
         ptx::fence_proxy_async_smem();

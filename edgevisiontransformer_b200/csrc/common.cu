@@ -114,6 +114,26 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
   return EVT_OK;
 }
 
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols, int swizzle_bytes) {
+  if (swizzle_bytes == 128) return make_tmap_2d(out, base, elem_bytes, rows, cols, ld, box_rows, box_cols);
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(EVT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(EVT_ERR_INVALID, "TMA base pointer not 16-byte aligned");
+  if ((ld * elem_bytes) % 16 != 0) return fail(EVT_ERR_INVALID, "TMA leading dimension not a multiple of 16 bytes");
+  if (swizzle_bytes != 64 || box_cols * elem_bytes != 64 || box_rows > 256 || box_rows == 0 || (elem_bytes != 2 && elem_bytes != 4))
+    return fail(EVT_ERR_INVALID, "TMA box must be as wide as its swizzle span (64 or 128 bytes) and at most 256 rows");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EVT_ERR_CUDA, "cuTensorMapEncodeTiled (64B swizzle) failed with CUresult " + std::to_string((int)r));
+  return EVT_OK;
+}
+
 int make_tmap_3d_rows(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t batch,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode();

@@ -93,6 +93,9 @@ int gemm_pair_mode();  // -1 auto, 0 never, 1 whenever applicable (evt_gemm_set_
 // box = box_rows x box_cols, 128-byte swizzle (box_cols * elem_bytes must be 128).
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols);
+// Same with a 64-byte swizzle span (box_cols * elem_bytes == 64): narrow staging tiles (swizzle_bytes 64 or 128).
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols, int swizzle_bytes);
 // 3-D view [batch][rows][cols] of a row-major matrix of batch * rows rows (leading dimension ld): a box is box_rows x
 // box_cols of ONE batch entry, so rows past the end of an image are zero-filled on loads and clipped on stores instead of
 // running into the next image.  128-byte swizzle.

@@ -303,21 +303,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         }
       }
       __syncwarp();
-      uint8_t* sb = stg + lane * 128;
+      // explicit st.shared: through the C++ pointer these were generic ST.E with descriptor set-up (see ptx.cuh)
+      const uint32_t sb = ptx::smem_u32(stg) + lane * 128;
       if constexpr (OUT_F32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(sb + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 8; ++i) ptx::sts_f4(sb + ((i ^ sw) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 w;
-          w.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-          w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-          w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-          *reinterpret_cast<uint4*>(sb + ((i ^ sw) << 4)) = w;
-        }
+        for (int i = 0; i < 8; ++i)
+          ptx::sts_u4(sb + ((i ^ sw) << 4), pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                      pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
       }
       if constexpr (TMA_OUT) {
         // The TMA engine does the coalescing, the M/N clipping and (for the skip connection) the f32 add into

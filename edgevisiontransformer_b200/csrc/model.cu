@@ -552,6 +552,10 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
 #else
   constexpr bool fuse_ln = false;  // gemm3.cu is only built with EVT_EXPERIMENTAL=1 (edgevisiontransformer_b200/build.py)
 #endif
+  // Narrow residual streams at large batch (D = 192 / 384: DeiT-Tiny / -Small, T2T): whole rows of a 256-row block fit in tensor
+  // memory, so the LayerNorm that FOLLOWS each residual projection runs in that projection's epilogue (gemm_rowln.cu): 5 launches
+  // per layer instead of 7 and the LayerNorm kernel's read of the f32 residual stream never happens.
+  const bool row_ln = !tf32 && !fuse_ln && gemm_rowln_supported(M, D, D);
   bool xn_ready = false;  // w.xn already holds LN1 of the current layer (written by the previous layer's FC2 epilogue)
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
@@ -559,7 +563,7 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
     // Narrow residual streams at large batch (D <= 384: DeiT-Tiny / -Small, T2T): the LayerNorm runs inside the projection
     // that consumes it, as the producer of its A operand (gemm_ln.cu) -- 5 launches per layer instead of 7, and the bf16
     // copy of the normalised rows never goes to HBM.
-    const bool ln_in_gemm = !tf32 && !fuse_ln && gemm_ln_supported(M, 3 * a, D);
+    const bool ln_in_gemm = !tf32 && !fuse_ln && !row_ln && gemm_ln_supported(M, 3 * a, D);
     if (ln_in_gemm) {
       EVT_STAGE(EVT_STAGE_QKV, gemm_ln_launch(w.resid, D, lw.ln1_g, lw.ln1_b, s.eps, tf ? w.resid : nullptr, lw.wqkv, D, lw.bqkv, w.qkv,
                                               3 * a, M, 3 * a, D, EVT_ACT_NONE, st));
@@ -586,7 +590,9 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_res_ln_launch(ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
     } else
 #endif
-    {
+    if (row_ln) {
+      EVT_STAGE(EVT_STAGE_OPROJ, gemm_rowln_launch(ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, tf, w.xn, D, M, D, a, st));
+    } else {
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
                           EVT_ACT_NONE, st));
       if (!ln_in_gemm)
@@ -606,7 +612,12 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
       xn_ready = true;
     } else
 #endif
-    {
+    if (row_ln && l + 1 < s.layers) {
+      const LayerW& nx = m->layers[l + 1];
+      EVT_STAGE(EVT_STAGE_FC2, gemm_rowln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, tf, w.xn,
+                                                 D, M, D, lw.inter, st));
+      xn_ready = true;
+    } else {
       EVT_STAGE(EVT_STAGE_FC2, gemm_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, dt, lw.b2, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M,
                           D, lw.inter, EVT_ACT_NONE, st));
     }
@@ -686,6 +697,21 @@ extern "C" int evt_model_forward_embedded(evt_model* m, const void* patch_matrix
   return forward_impl(m, nullptr, nullptr, patch_matrix, ld, batch, logits, workspace, workspace_bytes, stream);
 }
 
+extern "C" int evt_gemm_residual_layernorm_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid,
+                                              int64_t ldr, const float* gamma, const float* beta, float eps, int copy_ln, void* xn,
+                                              int64_t ldxn, int64_t M, int N, int K, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  EVT_CHECK_ARG(A != nullptr && W != nullptr && resid != nullptr && xn != nullptr && gamma != nullptr && beta != nullptr,
+                "gemm_residual_layernorm: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gemm_rowln_supported(M, N, K))
+    return gemm_rowln_launch(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, copy_ln != 0, xn, ldxn, M, N, K, st);
+  rc = gemm_launch(A, lda, W, ldw, EVT_BF16, bias, resid, ldr, 0, 0, resid, EVT_F32, ldr, 0, 0, 0, M, N, K, EVT_ACT_NONE, st);
+  if (rc != EVT_OK) return rc;
+  return layernorm_launch(resid, ldr, gamma, beta, xn, EVT_BF16, ldxn, copy_ln ? resid : nullptr, M, N, eps, st);
+}
+
 #ifndef EVT_EXPERIMENTAL
 // The single-kernel version (gemm3.cu) measured slower than the two kernels it replaces (negative results) and is
 // only built with EVT_EXPERIMENTAL=1; the entry point keeps its contract by issuing those two kernels.
@@ -696,9 +722,6 @@ extern "C" int evt_gemm_residual_layernorm(const void* A, int64_t lda, const voi
   if (rc != EVT_OK) return rc;
   EVT_CHECK_ARG(resid != nullptr && xn != nullptr && gamma != nullptr && beta != nullptr, "gemm_residual_layernorm: null pointer");
   if (N % 64 != 0 || N < 64 || N > 1024) return fail(EVT_ERR_UNSUPPORTED, "gemm+ln: N must be a multiple of 64 in [64, 1024]");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = gemm_launch(A, lda, W, ldw, EVT_BF16, bias, resid, ldr, 0, 0, resid, EVT_F32, ldr, 0, 0, 0, M, N, K, EVT_ACT_NONE, st);
-  if (rc != EVT_OK) return rc;
-  return layernorm_launch(resid, ldr, gamma, beta, xn, EVT_BF16, ldxn, nullptr, M, N, eps, st);
+  return evt_gemm_residual_layernorm_ex(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, 0, xn, ldxn, M, N, K, stream);
 }
 #endif

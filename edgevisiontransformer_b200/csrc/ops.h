@@ -15,6 +15,13 @@ int gemm_res_ln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, c
                        const float* gamma, const float* beta, float eps, void* xn, int64_t ldxn, int64_t M, int N, int K,
                        cudaStream_t stream);
 
+// The same for row lengths 192 / 384 with whole rows resident in tensor memory (gemm_rowln.cu); copy_ln: the residual stream
+// receives the normalised rows (TF dialect).  Supported = large M only (every CTA pair gets a 256-row block).
+bool gemm_rowln_supported(int64_t M, int N, int K);
+int gemm_rowln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid, int64_t ldr,
+                      const float* gamma, const float* beta, float eps, bool copy_ln, void* xn, int64_t ldxn, int64_t M, int N,
+                      int K, cudaStream_t stream);
+
 // LayerNorm fused into the A-operand producer of the following projection (gemm_ln.cu); K = D in {64,128,192,256,384}
 bool gemm_ln_supported(int64_t M, int N, int K);
 int gemm_ln_launch(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* x_copy, const void* W,

@@ -148,9 +148,10 @@ def layernorm_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, e
 
 def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor,
                               gamma: torch.Tensor, beta: torch.Tensor, eps: float, k: Optional[int] = None,
-                              xn: Optional[torch.Tensor] = None) -> torch.Tensor:
+                              xn: Optional[torch.Tensor] = None, copy_ln: bool = False) -> torch.Tensor:
     """resid[M,N] += a[M,K] @ w[N,K]^T + bias (f32, in place); returns xn = LayerNorm(resid) * gamma + beta (bf16).
-    One kernel: the LayerNorm runs in the GEMM epilogue (N a multiple of 64, <= 1024)."""
+    N = 192 / 384 at large M: one kernel, the LayerNorm runs in the GEMM epilogue on rows held in tensor memory; otherwise the
+    GEMM and the LayerNorm kernel.  copy_ln (TF dialect): resid ends up holding the normalised rows (f32)."""
     _need_cuda(a, w, bias, resid, gamma, beta, xn)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or resid.dtype != torch.float32:
         raise ValueError("linear_residual_layernorm wants bf16 operands and an f32 residual stream")
@@ -163,9 +164,9 @@ def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: Optional[t
     if xn is None:
         xn = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     lib = _lib.load()
-    rc = lib.evt_gemm_residual_layernorm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), resid.data_ptr(),
-                                         resid.stride(0), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
-                                         float(eps), xn.data_ptr(), xn.stride(0), M, N, K, _stream())
+    rc = lib.evt_gemm_residual_layernorm_ex(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), resid.data_ptr(),
+                                            resid.stride(0), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                            float(eps), int(copy_ln), xn.data_ptr(), xn.stride(0), M, N, K, _stream())
     _lib.check(rc, "gemm_residual_layernorm")
     return xn
 

@@ -137,6 +137,14 @@ int evt_layernorm_gemm(const float* x, int64_t ldx, const float* gamma, const fl
 int evt_gemm_residual_layernorm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                                 float* resid, int64_t ldr, const float* gamma, const float* beta, float eps,
                                 void* xn, int64_t ldxn, int64_t M, int N, int K, evt_stream stream);
+/* Same, with the reference's TF dialect as an option: copy_ln != 0 makes the residual stream receive the (unrounded f32)
+ * normalised rows instead of the sum (modeling/models/vit.py: the skip connection starts from LN(x)).  For N = 192 or 384 and
+ * enough rows to give every CTA pair a 256-row block this is ONE kernel that keeps whole rows in tensor memory
+ * (csrc/gemm_rowln.cu: the old residual arrives through a TMA ring, the LayerNorm passes read TMEM only); other shapes issue
+ * evt_gemm_bias_act + evt_layernorm_fwd.  Any N >= 1 with ldr, ldxn >= N. */
+int evt_gemm_residual_layernorm_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                   float* resid, int64_t ldr, const float* gamma, const float* beta, float eps, int copy_ln,
+                                   void* xn, int64_t ldxn, int64_t M, int N, int K, evt_stream stream);
 
 /* Fused softmax(Q K^T * scale) V for short sequences (S <= 256, head size 64):
  * eager_attention_forward SITE/models/vit/modeling_vit.py:171-196 ==

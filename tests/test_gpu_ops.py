@@ -173,6 +173,58 @@ def test_gemm_residual_layernorm_fused(M, N, K):
     assert (xn.float() - want_xn).abs().max().item() < 4e-2
 
 
+@pytest.mark.parametrize("M,N,K,copy_ln", [(256 * 80 + 129, 192, 64, False), (256 * 90 + 1, 192, 230, False), (256 * 75, 384, 384, False),
+                                         (256 * 74 + 255, 384, 1536, False), (256 * 80 + 129, 192, 230, True),
+                                         (256 * 77 + 33, 384, 1152, True), (197 * 1024, 192, 64, False)])
+def test_gemm_residual_layernorm_rows_in_tmem(M, N, K, copy_ln):
+    """csrc/gemm_rowln.cu (N = 192 / 384, every CTA pair gets a 256-row block): the new residual stream is bit-identical to the
+    TMA reduce-add GEMM (same accumulation, same single f32 add), the normalised rows match the LayerNorm of that stream, and
+    the TF dialect (copy_ln) leaves the unrounded normalised rows in the stream.  Row tails, K tails (230) and K = 64 included."""
+    ops = _ops()
+    ld = (K + 7) // 8 * 8
+    a = torch.zeros((M, ld), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((N, ld), dtype=torch.bfloat16, device="cuda")
+    a[:, :K] = _rand((M, K), 31).bfloat16()
+    w[:, :K] = _rand((N, K), 32, 0.05).bfloat16()
+    bias = _rand((N,), 33, 0.1)
+    res0 = _rand((M, N), 34) + 0.5 * _rand((M, 1), 35)
+    res0[:, 7] += 40.0                                         # an outlier channel, as trained ViTs have
+    gamma = 1 + _rand((N,), 36, 0.1)
+    beta = _rand((N,), 37, 0.1)
+    eps = 1e-5 if copy_ln else 1e-12
+    res = res0.clone()
+    canary = torch.full((64, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    xn_buf = torch.cat([torch.empty((M, N), dtype=torch.bfloat16, device="cuda"), canary])
+    xn = ops.linear_residual_layernorm(a, w, bias, res, gamma, beta, eps, k=K, xn=xn_buf[:M], copy_ln=copy_ln)
+    unfused = res0.clone()
+    ops.linear(a, w, bias, residual=unfused, out=unfused, out_dtype=torch.float32, k=K)
+    torch.cuda.synchronize()
+    assert torch.equal(xn_buf[M:], canary)                     # nothing written past row M
+    ref_xn = torch.nn.functional.layer_norm(unfused, (N,), gamma, beta, eps)
+    if copy_ln:
+        assert (res - ref_xn).abs().max().item() < 2e-4 * max(1.0, ref_xn.abs().max().item())
+        assert torch.equal(xn, res.bfloat16())
+    else:
+        assert torch.equal(res, unfused)
+        assert (xn.float() - ref_xn).abs().max().item() < 1e-2 * max(1.0, ref_xn.abs().max().item())
+        assert (xn.float() - ref_xn.bfloat16().float()).abs().mean().item() < 1e-3
+    want = res0 + a[:, :K].float() @ w[:, :K].float().t() + bias
+    assert (unfused - want).abs().max().item() < 2e-3 * max(1.0, math.sqrt(K) * 0.05)
+
+
+def test_gemm_residual_layernorm_rows_in_tmem_constant_rows():
+    """Exactly constant rows with eps = 1e-12: the centred variance is exactly 0, so xn == beta (no NaN / inf)."""
+    ops = _ops()
+    M, N, K = 256 * 80, 192, 64
+    a = torch.zeros((M, K), dtype=torch.bfloat16, device="cuda")
+    w = _rand((N, K), 41, 0.05).bfloat16()
+    res = torch.full((M, N), 3.25, device="cuda")
+    gamma, beta = 1 + _rand((N,), 42, 0.1), _rand((N,), 43, 0.1)
+    xn = ops.linear_residual_layernorm(a, w, None, res, gamma, beta, 1e-12)
+    assert torch.isfinite(xn.float()).all()
+    assert (xn.float() - beta.bfloat16().float()).abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("M,N,K,act", [(128 * 3 + 5, 576, 192, None), (1000, 230, 192, "gelu_erf"), (777, 1152, 384, None),
                                        (300, 1536, 384, "gelu_erf"), (130, 192, 64, "gelu_tanh"), (515, 768, 256, "gelu_tanh"),
                                        (128 * 150 + 77, 192, 192, None), (64, 100, 128, None)])

@@ -1,44 +1,56 @@
-"""Kernel shares from an `ncu --metrics gpu__time_duration.sum --csv --log-file X.csv` launch list (no GPU needed).
-
-    python tools/launch_shares.py gpurun_out/launches.csv [--md]
-"""
-import collections
+"""Split an ncu launch list (`--metrics gpu__time_duration.sum --csv`) of tools/profile_models.py at the `sign_` marker kernels
+and print, per model, the kernel shares of ONE forward as a markdown table.
+    python tools/launch_shares.py gpurun_out/models_launches.csv swin_tiny t2t_vit_14 pruned_tiny deit_small > profiles/rNN_model_shares.md"""
 import csv
 import re
 import sys
+from collections import OrderedDict
 
 
-def shares(path):
-    with open(path) as f:
+def rows(path):
+    with open(path, newline="") as f:
         lines = [l for l in f if not l.startswith("==")]
-    agg = collections.OrderedDict()
-    order = []
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
+    rd = csv.DictReader(lines)
+    for r in rd:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        k = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "").replace("unnamed>::", "").replace("evt::<", "")
-        v = float(row["Metric Value"].replace(",", ""))
-        u = row["Metric Unit"]
-        v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
-        a = agg.setdefault(k, [0, 0.0])
-        a[0] += 1
-        a[1] += v
-        order.append((k, v))
-    return agg, order
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        us = v / 1e3 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1e3
+        yield r["Kernel Name"], us
+
+
+def short(name):
+    name = re.sub(r"\(anonymous namespace\)::", "", name)
+    name = re.sub(r"^void ", "", name)
+    name = re.sub(r"\(.*\)$", "", name)
+    return name.replace("evt::", "")
+
+
+def main():
+    path, names = sys.argv[1], sys.argv[2:]
+    segs, cur, marks = [], [], 0
+    for k, us in rows(path):
+        if "sign_kernel_cuda" in k:
+            marks += 1
+            if marks % 2 == 0:
+                segs.append(cur)
+            cur = []
+            continue
+        cur.append((short(k), us))
+    print("# Kernel shares of one forward per model (ncu launch list, serialised launches at boost clocks: compare shares)\n")
+    for name, seg in zip(names, segs):
+        agg = OrderedDict()
+        for k, us in seg:
+            n, t = agg.get(k, (0, 0.0))
+            agg[k] = (n + 1, t + us)
+        tot = sum(t for _, t in agg.values())
+        print(f"## {name}: {len(seg)} launches, {tot / 1e3:.3f} ms summed\n")
+        print("| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"| `{k}` | {n} | {t:.1f} | {100 * t / tot:.1f} % | {t / n:.1f} |")
+        print()
 
 
 if __name__ == "__main__":
-    agg, order = shares(sys.argv[1])
-    tot = sum(a[1] for a in agg.values())
-    md = "--md" in sys.argv
-    print(f"{len(order)} launches, {tot:.1f} us")
-    if md:
-        print("| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|")
-    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        if md:
-            print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {a[1] / tot * 100:.1f} % | {a[1] / a[0]:.1f} |")
-        else:
-            print(f"{k[:72]:72s} {a[0]:4d} {a[1]:10.1f} {a[1] / tot * 100:5.1f}% {a[1] / a[0]:8.1f}")
-    if "--seq" in sys.argv:
-        for k, v in order:
-            print(f"{v:9.1f}  {k[:90]}")
+    main()
