@@ -555,7 +555,7 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
   // Narrow residual streams at large batch (D = 192 / 384: DeiT-Tiny / -Small, T2T): whole rows of a 256-row block fit in tensor
   // memory, so the LayerNorm that FOLLOWS each residual projection runs in that projection's epilogue (gemm_rowln.cu): 5 launches
   // per layer instead of 7 and the LayerNorm kernel's read of the f32 residual stream never happens.
-  const bool row_ln = !tf32 && !fuse_ln && gemm_rowln_supported(M, D, D);
+  const bool row_ln = !tf32 && !fuse_ln && gemm_rowln_supported(M, D, D, tf);  // per projection: gemm_rowln_pays
   bool xn_ready = false;  // w.xn already holds LN1 of the current layer (written by the previous layer's FC2 epilogue)
   for (int l = 0; l < s.layers; ++l) {
     const LayerW& lw = m->layers[l];
@@ -590,7 +590,7 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_res_ln_launch(ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, w.xn, D, M, D, a, st));
     } else
 #endif
-    if (row_ln) {
+    if (row_ln && gemm_rowln_pays(D, a, tf)) {
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_rowln_launch(ctx, a, lw.wo, a, lw.bo, w.resid, D, lw.ln2_g, lw.ln2_b, s.eps, tf, w.xn, D, M, D, a, st));
     } else {
       EVT_STAGE(EVT_STAGE_OPROJ, gemm_launch(ctx, a, lw.wo, a, dt, lw.bo, w.resid, D, 0, 0, w.resid, EVT_F32, D, 0, 0, 0, M, D, a,
@@ -612,7 +612,7 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
       xn_ready = true;
     } else
 #endif
-    if (row_ln && l + 1 < s.layers) {
+    if (row_ln && l + 1 < s.layers && gemm_rowln_pays(D, lw.inter, tf)) {
       const LayerW& nx = m->layers[l + 1];
       EVT_STAGE(EVT_STAGE_FC2, gemm_rowln_launch(w.big, lw.inter_ld, lw.w2, lw.inter_ld, lw.b2, w.resid, D, nx.ln1_g, nx.ln1_b, s.eps, tf, w.xn,
                                                  D, M, D, lw.inter, st));
@@ -705,7 +705,7 @@ extern "C" int evt_gemm_residual_layernorm_ex(const void* A, int64_t lda, const 
   EVT_CHECK_ARG(A != nullptr && W != nullptr && resid != nullptr && xn != nullptr && gamma != nullptr && beta != nullptr,
                 "gemm_residual_layernorm: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gemm_rowln_supported(M, N, K))
+  if (gemm_rowln_supported(M, N, K, copy_ln != 0))
     return gemm_rowln_launch(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, copy_ln != 0, xn, ldxn, M, N, K, st);
   rc = gemm_launch(A, lda, W, ldw, EVT_BF16, bias, resid, ldr, 0, 0, resid, EVT_F32, ldr, 0, 0, 0, M, N, K, EVT_ACT_NONE, st);
   if (rc != EVT_OK) return rc;

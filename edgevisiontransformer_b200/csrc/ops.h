@@ -17,7 +17,8 @@ int gemm_res_ln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, c
 
 // The same for row lengths 192 / 384 with whole rows resident in tensor memory (gemm_rowln.cu); copy_ln: the residual stream
 // receives the normalised rows (TF dialect).  Supported = large M only (every CTA pair gets a 256-row block).
-bool gemm_rowln_supported(int64_t M, int N, int K);
+bool gemm_rowln_supported(int64_t M, int N, int K, bool copy_ln);
+bool gemm_rowln_pays(int N, int K, bool copy_ln);  // model runtime: the fused kernel beats GEMM + LayerNorm for this projection
 int gemm_rowln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid, int64_t ldr,
                       const float* gamma, const float* beta, float eps, bool copy_ln, void* xn, int64_t ldxn, int64_t M, int N,
                       int K, cudaStream_t stream);

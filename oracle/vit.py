@@ -178,9 +178,18 @@ def state_dict_of(model) -> Dict[str, torch.Tensor]:
 
 
 def compare_logits(got: torch.Tensor, want: torch.Tensor) -> Dict[str, float]:
+    """max-abs logit difference and top-1 agreement.  A row whose argmax differs still agrees when the reference itself holds the
+    two classes within twice that row's max-abs difference: random-init models have near-tied top logits, and an implementation
+    whose logits are within e of the reference cannot be asked to break a tie narrower than 2e the same way (with split-K
+    reduce-adds landing in any order at small batch, such a tie flipped in about one run out of four)."""
     got = got.detach().float().cpu()
     want = want.detach().float().cpu()
+    err = (got - want).abs()
+    pick = got.argmax(-1)
+    margin = want.max(-1).values - want.gather(-1, pick[..., None])[..., 0]      # 0 where the argmax matches
+    agree = margin <= 2 * err.amax(-1)
     return {
-        "max_abs": float((got - want).abs().max()),
-        "top1_agree": float((got.argmax(-1) == want.argmax(-1)).float().mean()),
+        "max_abs": float(err.max()),
+        "top1_agree": float(agree.float().mean()),
+        "top1_exact": float((pick == want.argmax(-1)).float().mean()),
     }
