@@ -182,6 +182,15 @@ def test_t2t_front_end_and_model():
     for _ in range(2):                                   # latency path: one CUDA graph over front-end + encoder
         r = ovit.compare_logits(m.forward_graphed(x.cuda()).logits, want_logits)
         assert r["max_abs"] <= BF16_TOL and r["top1_agree"] == 1.0, r
+    # a larger batch makes the core reallocate its workspace: graphs captured over the old one must not be replayed
+    small = m.forward_graphed(x.cuda()).logits.clone()
+    big = ovit.synthetic_images(8, seed=5, channels_last=True).cuda()
+    big_eager = m(big).logits.clone()
+    again = m.forward_graphed(x.cuda()).logits
+    r = ovit.compare_logits(again, small)
+    assert r["max_abs"] <= BF16_TOL, r                   # same numbers as before the reallocation up to the split-K reduce order
+    r = ovit.compare_logits(m(big).logits, big_eager)    # and the replay did not scribble over anything the eager path uses
+    assert r["max_abs"] <= BF16_TOL, r
 
 
 def test_stage_profile_tap():
