@@ -301,7 +301,10 @@ int evt_model_forward_ex(evt_model* m, const void* pixels, const evt_forward_opt
  * (tokens-to-token module, modeling/models/t2t_vit.py:63-88), whose last soft split produces exactly that matrix. */
 int evt_model_forward_embedded(evt_model* m, const void* patch_matrix, int64_t ld, int batch, float* logits,
                                void* workspace, size_t workspace_bytes, evt_stream stream);
-/* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
+/* Number of kernel launches one forward issues at small batch (3 + 7 per layer + head; T2T front-end extra).  At large batch
+ * a model with hidden size 192 or 384 issues up to two fewer per layer: the LayerNorm that follows a residual projection runs
+ * in that projection's epilogue (evt_gemm_residual_layernorm_ex).  evt_launch_count() reports what was actually launched;
+ * bench.py's gpu_launches is taken from it. */
 int evt_model_launches_per_forward(const evt_model* m);
 /* Measurement aid (bench.py's roofline): between begin and end every forward on `m` records a CUDA event on its
  * stream before its first launch and after every launch.  end synchronises on the last event, adds the elapsed time
