@@ -222,9 +222,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, bool OUT_F32, int ACT>
-int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, GemmParams p, cudaStream_t stream) {
-  constexpr int EW = (ACT != EVT_ACT_NONE && !OUT_F32) ? kEpiWarpsAct : 8;
+template <int BN, bool OUT_F32, int ACT, int EW>
+int launch_pair_ew(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, GemmParams p, cudaStream_t stream) {
   using C = Cfg2<BN, EW>;
   constexpr int kThreads = C::kThreadsCta;
   auto kern = gemm_pair_kernel<BN, OUT_F32, ACT, EW>;
@@ -255,6 +254,22 @@ int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtens
   EVT_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, pdl_for_gemm(p.M, p.N, p.K), tmA, tmW, tmO, p));
   EVT_LAUNCH_CHECK("gemm_pair_kernel");
   return EVT_OK;
+}
+
+// Epilogue warps per CTA.  With a fused activation and a SHORT K loop (K <= 384: DeiT-Tiny / -Small / T2T FC1, three to six
+// k-blocks per tile) the tile time is the epilogue's, and sixteen warps (four per TMEM lane quadrant, one 64-column chunk each)
+// finish it sooner: FC1 74.6 -> 68.9 us at D = 384 (batch 256), 49.1 -> 45.2 us for the pruned Tiny (batch 1024), same box.  With
+// a long K loop the MMAs bound the tile and sixteen warps LOSE (DeiT-Base FC1 0.944 vs 0.912 ms: 96 registers per thread, one
+// pipeline stage less), so eight stay the default there.  Without an activation sixteen warps lose as well (QKV at D = 384:
+// 55 vs 49 us): the plain bf16 epilogue is bound by its TMA stores, not by instruction latency.
+template <int BN, bool OUT_F32, int ACT>
+int launch_pair(const void* W, int64_t ldw, const CUtensorMap& tmA, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (ACT != EVT_ACT_NONE && !OUT_F32) {
+    if (kEpiWarpsAct == 8 && p.K <= 384) return launch_pair_ew<BN, OUT_F32, ACT, 16>(W, ldw, tmA, tmO, p, stream);
+    return launch_pair_ew<BN, OUT_F32, ACT, kEpiWarpsAct>(W, ldw, tmA, tmO, p, stream);
+  } else {
+    return launch_pair_ew<BN, OUT_F32, ACT, 8>(W, ldw, tmA, tmO, p, stream);
+  }
 }
 
 template <int BN>
