@@ -14,8 +14,29 @@ from typing import Dict, Iterable, Optional
 import torch
 
 
+class PendingLogits:
+    """Handle of one `PipelinedClassifier.submit` call: the copies and launches are queued, `result()` waits for them."""
+
+    def __init__(self, dev_out, host_out, done):
+        self._dev_out, self._host_out, self._done = dev_out, host_out, done
+
+    def done(self) -> bool:
+        return self._done.query()
+
+    def result(self) -> torch.Tensor:
+        """[B, num_labels] f32 on the HOST.  With pinned input this is one of the runner's two pinned result buffers for the
+        batch size: valid until the second-next submit of that size (clone it to keep it longer)."""
+        self._done.synchronize()
+        return self._host_out if self._host_out is not None else self._dev_out.cpu()
+
+
 class PipelinedClassifier:
-    """Runs a B200ViTForImageClassification over a HOST batch in chunks, double-buffering the H2D copies."""
+    """Runs a B200ViTForImageClassification over a HOST batch in chunks, double-buffering the H2D copies.
+
+    `logits(host)` is the synchronous call; `submit(host)` queues the same work and returns a handle, so an evaluation loop can
+    queue batch i+1 before it collects batch i -- the H2D copies of the next batch then run under the last forwards of the
+    current one (the staging buffers are guarded by events, not by a synchronise), which is what a DataLoader-fed loop with
+    non-blocking copies does in the reference (deit_pruning/src/utils.py:188-199)."""
 
     def __init__(self, model, chunk: int = 512):
         self.model = model
@@ -29,9 +50,11 @@ class PipelinedClassifier:
         self._free = [torch.cuda.Event() for _ in range(2)]
         self._host_out = None
         self._pinned_out = {}
+        self._pinned_sel = {}
+        self._last = None              # handle of the most recent submit (steady state = it is still running)
 
     @torch.no_grad()
-    def _run(self, host_pixels: torch.Tensor, want_logits: bool):
+    def _run(self, host_pixels: torch.Tensor, want_logits: bool, ramp: bool = True):
         if host_pixels.is_cuda:
             raise ValueError("PipelinedClassifier takes host tensors; call the model directly for device tensors")
         B = host_pixels.shape[0]
@@ -50,18 +73,22 @@ class PipelinedClassifier:
         # then full chunks): every later copy hides behind the forward of the chunk before it (a forward costs ~3x its
         # copy per image), and only the first small copy is exposed.
         bounds, s0 = [], 0
-        for n in chunk_schedule(B, self.chunk):
+        for n in (chunk_schedule(B, self.chunk) if ramp else uniform_schedule(B, self.chunk)):
             bounds.append((s0, s0 + n))
             s0 += n
         host_out = None
         if want_logits and host_pixels.is_pinned():
             # pinned result buffer, allocated once per batch size (cudaHostAlloc costs milliseconds); the caller owns the
             # returned tensor until the next call with the same batch size
-            host_out = self._pinned_out.get(B)
-            if host_out is None:
-                host_out = self._pinned_out[B] = torch.empty((B, c.num_labels), dtype=torch.float32).pin_memory()
-        for k in range(2):
-            self._free[k].record(main)
+            # two of them, alternating: the result of the previous submit may not have been collected yet
+            pair = self._pinned_out.get(B)
+            if pair is None:
+                pair = self._pinned_out[B] = [torch.empty((B, c.num_labels), dtype=torch.float32).pin_memory() for _ in range(2)]
+            sel = self._pinned_sel.get(B, 0)
+            self._pinned_sel[B] = sel ^ 1
+            host_out = pair[sel]
+        # (no re-recording of the `free` events here: each was last recorded after the forward that read its buffer, possibly
+        #  in the previous call -- waiting for exactly that forward is what lets this call's first copies start early)
         for i, (s, e) in enumerate(bounds):
             k = i & 1
             with torch.cuda.stream(self._copy_stream):
@@ -81,19 +108,39 @@ class PipelinedClassifier:
             self._host_out = host_out
         return out
 
+    def submit(self, host_pixels: torch.Tensor) -> PendingLogits:
+        """Queue H2D copies, forwards and the D2H of the logits for one host batch; returns without waiting.  At most two
+        submits may be outstanding (two pinned result buffers per batch size).  While the previous submit is still running
+        the chunks are uniform -- the geometric ramp only exists to shorten the one copy nothing can hide."""
+        steady = self._last is not None and not self._last.done()
+        self._host_out = None
+        dev_out = self._run(host_pixels, True, ramp=not steady)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        h = PendingLogits(dev_out, self._host_out, done)
+        self._host_out = None
+        self._last = h
+        return h
+
     def logits(self, host_pixels: torch.Tensor) -> torch.Tensor:
         """[B, num_labels] f32 on the HOST (synchronises)."""
-        self._host_out = None
-        dev_out = self._run(host_pixels, True)
-        if self._host_out is not None:                       # pinned input: chunk-wise async D2H already queued
-            torch.cuda.current_stream(self.device).synchronize()
-            out, self._host_out = self._host_out, None
-            return out.clone() if out.numel() < (1 << 22) else out   # small results: hand out a private copy
-        return dev_out.cpu()
+        out = self.submit(host_pixels).result()
+        return out.clone() if out.numel() < (1 << 22) else out      # small results: hand out a private copy
 
     def predict(self, host_pixels: torch.Tensor) -> torch.Tensor:
         """argmax class ids [B] on the HOST; only 8 bytes per image cross PCIe on the way back."""
         return self._run(host_pixels, False).cpu()
+
+
+def uniform_schedule(batch: int, chunk: int) -> list:
+    """Full chunks, a short tail (less than half a chunk) folded into the last one's neighbour by splitting evenly."""
+    n = max(1, -(-batch // chunk))
+    if n > 1 and batch - (n - 1) * chunk < chunk // 2:
+        n -= 1                                   # the tail rides on the last full chunk, split in two equal parts below
+        base = (n - 1) * chunk
+        rest = batch - base
+        return [chunk] * (n - 1) + ([rest] if rest <= chunk else [rest - rest // 2, rest // 2])
+    return [min(chunk, batch - i * chunk) for i in range(n)]
 
 
 def chunk_schedule(batch: int, chunk: int) -> list:
@@ -138,14 +185,20 @@ def evaluate(eval_data: Iterable, model, eval_batch_size: int = 100, device=None
     n_examples, n_steps, inference_time = 0, 0, 0.0
     for images, labels in loader:
         t0 = time.time()
-        lg = runner._run(images if not images.is_cuda else images.cpu(), True)
+        # Queued, not waited for: the staging buffers are guarded by events, so the copies of the next batch run under the last
+        # forwards of this one (and under the loader's work for the batch after).  `inference_time` is the time this loop spends
+        # queueing GPU work plus the final drain -- the reference's per-batch wall time (utils.py:190-199) without its per-batch
+        # synchronise.
+        lg = runner._run(images if not images.is_cuda else images.cpu(), True, ramp=(n_steps == 0))
         pred = lg.argmax(dim=-1)
         correct += (pred == labels.to(dev, non_blocking=True)).sum()
         loss_sum += lg.double().mean()
-        torch.cuda.current_stream(dev).synchronize()
         inference_time += time.time() - t0
         n_examples += images.shape[0]
         n_steps += 1
+    t0 = time.time()
+    torch.cuda.current_stream(dev).synchronize()
+    inference_time += time.time() - t0
     result = dict(result or {})
     result["eval_loss"] = float(loss_sum.item()) / max(n_steps, 1)
     result["eval_accuracy"] = float(correct.item()) / max(n_examples, 1)

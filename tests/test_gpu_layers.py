@@ -113,3 +113,18 @@ def test_eval_loop_matches_reference_evaluate_semantics():
         assert torch.equal(runner.predict(x.pin_memory()), lg.argmax(-1))
     finally:
         ops.set_gemm_split_k(True)
+    # submit / result: two batches in flight (the second one's copies start under the first one's forwards, staging buffers
+    # and pinned result buffers alternate): every handle returns the logits of ITS batch, in any collection order
+    xs = [ovit.synthetic_images(23, seed=20 + i).pin_memory() for i in range(4)]
+    wants = [runner.logits(xi).clone() for xi in xs]
+    h0 = runner.submit(xs[0])
+    h1 = runner.submit(xs[1])
+    r1, r0 = h1.result().clone(), h0.result().clone()
+    h2 = runner.submit(xs[2])
+    h3 = runner.submit(xs[3])
+    r2, r3 = h2.result().clone(), h3.result().clone()
+    for i, (got_i, want_i) in enumerate(zip((r0, r1, r2, r3), wants)):
+        # the same numbers up to the chunk schedule (uniform while another batch is in flight) and the split-K reduce order ...
+        assert ovit.compare_logits(got_i, want_i)["max_abs"] <= 2e-2
+        # ... and nobody else's: the batches differ from each other by far more than that
+        assert all(ovit.compare_logits(got_i, wants[j])["max_abs"] > 5e-2 for j in range(4) if j != i)
