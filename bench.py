@@ -436,19 +436,33 @@ def main():
         e2e_run.h2d_gbs = host.numel() * host.element_size() / step_s / 1e9     # per-GPU host -> device rate this implies
         return gbatch / step_s
 
-    host = torch.empty((per, 3, 224, 224), dtype=torch.float32).pin_memory()
+    # pinned host batches are allocated with the process bound to the GPU's own NUMA node (restored right after: the CPU
+    # baseline leg below must see every core)
+    from edgevisiontransformer_b200.eval_loop import near_gpu
+    with near_gpu(dev) as numa_note:
+        host = torch.empty((per, 3, 224, 224), dtype=torch.float32).pin_memory()
     host.copy_(x)
-    e2e_value = e2e_run(host)
+    e2e_pipe = e2e_run(host)
     e2e_h2d_gbs = e2e_run.h2d_gbs
     e2e_sync = e2e_run(host, pipelined=False)
+    # Both are the public API; the headline is the better one and says which.  One batch queued ahead wins when PCIe has
+    # headroom (1-2 GPUs: the one exposed copy per step disappears); with eight GPUs pulling f32 pixels at once the host side
+    # saturates (~100-115 GB/s aggregate on this pool's VMs) and the continuous copies of the queued-ahead loop fare worse
+    # than the bursts of the per-call loop -- bf16 / uint8 pixels (other_pixel_types) are the remedy there.
+    e2e_value, e2e_mode = (e2e_pipe, "pipelined") if e2e_pipe >= e2e_sync else (e2e_sync, "per_call_synchronous")
+    if e2e_mode != "pipelined":
+        e2e_h2d_gbs = e2e_run.h2d_gbs
     e2e_alt = {}
-    hb = torch.empty((per, 3, 224, 224), dtype=torch.bfloat16).pin_memory()
+    with near_gpu(dev):
+        hb = torch.empty((per, 3, 224, 224), dtype=torch.bfloat16).pin_memory()
     hb.copy_(x)
     del host
     e2e_alt["bf16_pixels"] = {"value": e2e_run(hb), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 2,
                               "h2d_gb_per_s_per_gpu": e2e_run.h2d_gbs}
     del hb
-    hu = torch.randint(0, 256, (per, 3, 224, 224), dtype=torch.uint8).pin_memory()
+    with near_gpu(dev):
+        hu = torch.empty((per, 3, 224, 224), dtype=torch.uint8).pin_memory()
+    hu.copy_(torch.randint(0, 256, (per, 3, 224, 224), dtype=torch.uint8))
     e2e_alt["u8_pixels"] = {"value": e2e_run(hu), "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224,
                             "h2d_gb_per_s_per_gpu": e2e_run.h2d_gbs,
                             "note": "raw uint8 images, ImageNet mean/std normalisation fused into the patch gather"}
@@ -544,8 +558,11 @@ def main():
                        "preroll": "%d untimed steps over %.1f s before the timed region (sustained clocks)" % (pre_steps, args.preroll_s)},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 4,
                     "d2h_bytes_per_step": per * 1000 * 4, "pixels": "f32 pinned host memory",
-                    "how": "PipelinedClassifier.submit/result, step i+1 queued before step i is collected (its H2D runs under "
-                           "step i's last forwards); every step copies its pixels in and its logits out inside the timed region",
+                    "host_numa": numa_note or "not bound (NVML affinity unavailable)",
+                    "mode": e2e_mode,
+                    "how": "every step copies its pixels in and its logits out inside the timed region; value = the better of the two loops below",
+                    "pipelined": {"value": e2e_pipe, "unit": "img/s", "how": "PipelinedClassifier.submit/result, step i+1 queued before "
+                                  "step i is collected (its H2D runs under step i's last forwards)"},
                     "per_call_synchronous": {"value": e2e_sync, "unit": "img/s", "how": "one PipelinedClassifier.logits(host) per step"},
                     "h2d_gb_per_s_per_gpu": e2e_h2d_gbs, "ratio_to_device_resident": e2e_value / value,
                     "other_pixel_types": e2e_alt},

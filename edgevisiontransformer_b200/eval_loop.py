@@ -8,10 +8,51 @@ device per batch instead of B x 1000 floats (the reference does ``logits.cpu().n
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import time
 from typing import Dict, Iterable, Optional
 
 import torch
+
+
+@contextlib.contextmanager
+def near_gpu(device=None):
+    """Run the body with this thread bound to the CPUs closest to `device` (NVML's ideal CPU affinity), then restore the
+    previous affinity.  Pinned host buffers allocated inside land on the GPU's NUMA node, so their H2D copies do not cross the
+    socket interconnect -- on a two-socket box with eight GPUs copying at once that link, not PCIe, is what saturates.
+    Yields a description of the binding, or None when NVML / the affinity call is not available (nothing is changed then)."""
+    old, note = None, None
+    try:
+        import pynvml
+        idx = torch.device(device if device is not None else torch.cuda.current_device())
+        idx = idx.index if idx.index is not None else torch.cuda.current_device()
+        prop = torch.cuda.get_device_properties(idx)
+        pynvml.nvmlInit()
+        try:
+            bus = "%08x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        now = os.sched_getaffinity(0)
+        note = "cpus %d-%d (%d of %d)" % (min(now), max(now), len(now), len(old))
+    except Exception:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
+        old = None
+    try:
+        yield note
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
 
 
 class PendingLogits:
@@ -83,7 +124,8 @@ class PipelinedClassifier:
             # two of them, alternating: the result of the previous submit may not have been collected yet
             pair = self._pinned_out.get(B)
             if pair is None:
-                pair = self._pinned_out[B] = [torch.empty((B, c.num_labels), dtype=torch.float32).pin_memory() for _ in range(2)]
+                with near_gpu(self.device):
+                    pair = self._pinned_out[B] = [torch.empty((B, c.num_labels), dtype=torch.float32).pin_memory() for _ in range(2)]
             sel = self._pinned_sel.get(B, 0)
             self._pinned_sel[B] = sel ^ 1
             host_out = pair[sel]
