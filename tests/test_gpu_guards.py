@@ -43,6 +43,25 @@ def test_layernorm_stays_in_bounds(rows, D):
         y.check(f"layernorm {rows}x{D} {dt}")
 
 
+@pytest.mark.parametrize("M,N,K,copy_ln", [(256 * 74 + 129, 192, 64, False), (256 * 74 + 1, 192, 230, True), (256 * 74 + 33, 384, 384, False),
+                                         (256 * 75 + 255, 384, 200, True)])
+def test_projection_layernorm_rows_in_tmem_stays_in_bounds(M, N, K, copy_ln):
+    """csrc/gemm_rowln.cu with row tails of 129 / 1 / 33 / 255 rows in the last 256-row block: the residual stream (updated in
+    place through TMA stores from the ring tiles) and the normalised rows must not reach past row M; rows below M all written."""
+    L, lib = _lib()
+    ld = (K + 7) // 8 * 8
+    a = torch.randn(M, ld, device="cuda").bfloat16()
+    w = (torch.randn(N, ld, device="cuda") * 0.05).bfloat16()
+    bias, g, b = torch.randn(N, device="cuda"), torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+    res, xn = Guarded(M * N, torch.float32), Guarded(M * N, torch.bfloat16)
+    res.out.copy_(torch.randn(M * N, device="cuda"))
+    L.check(lib.evt_gemm_residual_layernorm_ex(a.data_ptr(), ld, w.data_ptr(), ld, bias.data_ptr(), res.out.data_ptr(), N, g.data_ptr(),
+                                               b.data_ptr(), 1e-5, int(copy_ln), xn.out.data_ptr(), N, M, N, K, _st()))
+    res.check(f"gemm+ln residual {M}x{N} K={K}")
+    xn.check(f"gemm+ln normalised rows {M}x{N} K={K}")
+    assert torch.isfinite(res.out).all() and torch.isfinite(xn.out.float()).all()
+
+
 @pytest.mark.parametrize("B,T_in,T_out,G,C", [(3, 196, 196, 1, 96), (1, 49, 49, 1, 96), (3, 196, 50, 1, 192), (2, 784, 196, 4, 192),
                                                (2, 196, 49, 4, 768), (1, 49, 49, 1, 384)])
 def test_gather_layernorm_stays_in_bounds(B, T_in, T_out, G, C):

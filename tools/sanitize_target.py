@@ -25,6 +25,14 @@ for (M, N, K) in [(197, 576, 192), (300, 768, 3072), (197, 230, 192), (256 * 3 +
     if N % 64 == 0:
         r = torch.randn(M, N, device="cuda")
         ops.linear_residual_layernorm(a, w, b, r, torch.ones(N, device="cuda"), torch.zeros(N, device="cuda"), 1e-12, k=K)
+# projection + LayerNorm with rows resident in tensor memory (gemm_rowln.cu): needs >= 74 row blocks of 256; row and K tails
+for (M, N, K, copy_ln) in [(256 * 74 + 129, 192, 64, False), (256 * 74 + 1, 192, 230, True), (256 * 74 + 33, 384, 384, False),
+                           (256 * 75, 384, 200, True)]:
+    a = torch.randn(M, (K + 7) // 8 * 8, device="cuda").bfloat16()
+    w = (torch.randn(N, (K + 7) // 8 * 8, device="cuda") * 0.05).bfloat16()
+    r = torch.randn(M, N, device="cuda")
+    ops.linear_residual_layernorm(a, w, torch.randn(N, device="cuda"), r, torch.ones(N, device="cuda"), torch.zeros(N, device="cuda"),
+                                  1e-5, k=K, copy_ln=copy_ln)
 for (B, S, H) in [(2, 197, 3), (1, 256, 2), (3, 128, 2), (2, 16, 1)]:
     qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
     ops.attention(qkv, B, S, H)
