@@ -111,8 +111,8 @@ struct Workspace {
   float* resid;
   uint8_t *xn, *qkv, *ctx, *big, *clsn, *hh;  // activations in the GEMM operand type (bf16, or f32 in tf32 mode)
   // T2T front-end (spec.t2t): per performer stage the unfolded + normalised rows, k|q|v, the attention output, the f32
-  // token stream y, LN(y), the MLP hidden rows and the performer scratch; `pm` = the patch matrix of the embedding GEMM
-  uint8_t *t_x[2], *t_kqv[2], *t_ya[2], *t_z[2], *t_h[2], *t_ws[2], *t_pm;
+  // token stream y and the performer scratch; `pm` = the patch matrix of the embedding GEMM
+  uint8_t *t_x[2], *t_kqv[2], *t_ya[2], *t_ws[2], *t_pm;
   float* t_y[2];
   size_t bytes;
 };
@@ -155,10 +155,9 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
       const size_t T = static_cast<size_t>(t2t_side(s.image, i)) * t2t_side(s.image, i) * batch;
       const size_t in_ld = i == 0 ? 152 : 576;
       const size_t ox = take(T * in_ld * 2), ok = take(T * 192 * 2), oa = take(T * 64 * 2), oy = take(T * 64 * 4);
-      const size_t oz = take(T * 64 * 2), oh = take(T * 64 * 2);
       const size_t ow = take(performer_workspace_bytes(batch, t2t_side(s.image, i) * t2t_side(s.image, i)));
       w.t_x[i] = b + ox, w.t_kqv[i] = b + ok, w.t_ya[i] = b + oa, w.t_y[i] = reinterpret_cast<float*>(b + oy);
-      w.t_z[i] = b + oz, w.t_h[i] = b + oh, w.t_ws[i] = b + ow;
+      w.t_ws[i] = b + ow;
     }
     w.t_pm = b + take(Mp * 576 * 2);
   }
@@ -437,8 +436,8 @@ extern "C" int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* 
 extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   if (!m) return 0;
   const evt_model_spec& s = m->spec;
-  // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels, attn_output, LN, fc1, fc2; then the last soft split
-  return (s.t2t ? 2 * 9 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+  // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels, the fused attn_output + MLP tail; then the last soft split
+  return (s.t2t ? 2 * 6 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
 static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts* opts, const void* patch_matrix, int64_t patch_ld,
@@ -506,15 +505,8 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
                                              0, 0, 0, rows, 192, pw.in_dim, EVT_ACT_NONE, st));
       EVT_TRY(performer_launch(w.t_kqv[i], 192, pw.w, w.t_ya[i], w.t_y[i], w.t_ws[i], batch, T, 64, 32, 1e-8f, st));
       EVT_TRY(mark(EVT_STAGE_EMBED));
-      // y = v + attn_output(.)   (transformer_encoder.py:93)
-      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_ya[i], 64, pw.wo, 64, EVT_BF16, pw.bo, w.t_y[i], 64, 0, 0, w.t_y[i], EVT_F32, 64, 0, 0, 0, rows,
-                                             64, 64, EVT_ACT_NONE, st));
-      EVT_STAGE(EVT_STAGE_EMBED, layernorm_launch(w.t_y[i], 64, pw.g2, pw.b2, w.t_z[i], EVT_BF16, 64, nullptr, rows, 64, tf_eps, st));
-      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_z[i], 64, pw.w1, 64, EVT_BF16, pw.bb1, nullptr, 0, 0, 0, w.t_h[i], EVT_BF16, 64, 0, 0, 0, rows, 64,
-                                             64, EVT_ACT_GELU_TANH, st));
-      // y += mlp(LN(y))   (:99)
-      EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_h[i], 64, pw.w2, 64, EVT_BF16, pw.bb2, w.t_y[i], 64, 0, 0, w.t_y[i], EVT_F32, 64, 0, 0, 0, rows,
-                                             64, 64, EVT_ACT_NONE, st));
+      // y = v + attn_output(.) ; y += mlp(LN(y))   (transformer_encoder.py:93-99): one kernel, 64-wide rows never leave the SM
+      EVT_STAGE(EVT_STAGE_EMBED, performer_mlp_launch(w.t_ya[i], w.t_y[i], pw.wo, pw.bo, pw.g2, pw.b2, pw.w1, pw.bb1, pw.w2, pw.bb2, rows, tf_eps, st));
       src = w.t_y[i], src_dt = EVT_F32, side = so, ch = 64;
     }
     EVT_STAGE(EVT_STAGE_EMBED, unfold_ln_launch(src, src_dt, w.t_pm, 576, nullptr, nullptr, tf_eps, batch, side, side, 64, 3, 2, 1, st));

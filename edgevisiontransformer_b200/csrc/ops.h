@@ -53,6 +53,10 @@ int unfold_ln_launch(const void* x, int x_dtype, void* out, int64_t ldo, const f
 size_t performer_workspace_bytes(int B, int T);
 int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace, int B, int T, int emb,
                      int m, float eps, cudaStream_t st);
+// y <- v + attn_output(ya); y += mlp(LayerNorm(y)) for 64-wide performer tokens: ya bf16 [rows, 64], y f32 [rows, 64] holding v on
+// entry; wo / w1 / w2 bf16 [64 out, 64 in] dense; tanh-GELU
+int performer_mlp_launch(const void* ya, float* y, const void* wo, const float* bo, const float* gamma, const float* beta, const void* w1,
+                         const float* b1, const void* w2, const float* b2, int64_t rows, float eps, cudaStream_t st);
 int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k, int s, int p,
                   cudaStream_t st);
 

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "gemm_common.cuh"
 #include "ops.h"
 #include "ptx.cuh"
 
@@ -141,6 +142,8 @@ __global__ void __launch_bounds__(256) unfold_ln_rows_kernel(const TIN* __restri
   long long t = row0 / ow;
   int oy = static_cast<int>(t % oh);
   long long b = t / oh;
+  // (unrolling this loop by 2 or 4 so that several rows' loads are in flight per warp measured no gain: T2T-ViT-14 batch 256
+  //  47.5-47.8 k against 48.1-48.4 k img/s, same box -- occupancy already hides the load latency)
 #pragma unroll 1
   for (int r = 0; r < ROWS; ++r) {
     const long long row = row0 + r;
@@ -463,6 +466,153 @@ __global__ void __launch_bounds__(128) performer_apply_kernel(const __nv_bfloat1
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- performer tail
+// Everything the Token_performer does after the attention contraction (modeling/layers/transformer_encoder.py:93-99), for 64-wide
+// tokens, in ONE pass over the rows:
+//     y  = v + attn_output(ya)            (Dense 64 -> 64; v = the f32 copy of the value rows the apply kernel wrote)
+//     y += mlp(LayerNorm(y))              (Dense 64 -> 64, tanh-GELU, Dense 64 -> 64)
+// Before: GEMM (f32 reduce-add), LayerNorm kernel, GEMM + GELU, GEMM (reduce-add) -- four launches moving 1920 bytes per token;
+// here 640 (ya in, y in, y out).  Per 16-token tile a warp chains three m16n8k16 products whose accumulator fragments are the
+// next product's A fragments (two adjacent n-tiles = one k-step), the LayerNorm statistics are quad reductions over the
+// accumulator fragment (f32, centred variance), the three 64 x 64 weights sit in shared memory with rows padded to 144 bytes
+// (conflict-free B-fragment loads).  Same arithmetic as the four kernels (bf16 operands, f32 accumulation, f32 skip), so the
+// results agree with them to summation order.
+constexpr int kWRow = 72;  // bf16 elements per padded weight row
+
+__global__ void __launch_bounds__(128) performer_mlp_kernel(const __nv_bfloat16* __restrict__ ya, float* __restrict__ y,
+                                                            const __nv_bfloat16* __restrict__ wo, const float* __restrict__ bo,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const __nv_bfloat16* __restrict__ w1, const float* __restrict__ b1,
+                                                            const __nv_bfloat16* __restrict__ w2, const float* __restrict__ b2,
+                                                            long long rows, float eps) {
+  __shared__ __align__(16) __nv_bfloat16 ws[3][kEmb * kWRow];
+  __shared__ __align__(16) float vec[5][kEmb];  // bo, gamma, beta, b1, b2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < 3 * kEmb * 8; i += 128) {  // 16-byte pieces: 8 per 64-element row
+    const int m = i / (kEmb * 8), r = (i / 8) % kEmb, c = i % 8;
+    const __nv_bfloat16* src = m == 0 ? wo : m == 1 ? w1 : w2;
+    *reinterpret_cast<uint4*>(&ws[m][r * kWRow + c * 8]) = *reinterpret_cast<const uint4*>(src + r * kEmb + c * 8);
+  }
+  for (int i = threadIdx.x; i < 5 * kEmb; i += 128) {
+    const int m = i / kEmb, c = i % kEmb;
+    const float* src = m == 0 ? bo : m == 1 ? gamma : m == 2 ? beta : m == 3 ? b1 : b2;
+    vec[m][c] = src != nullptr ? src[c] : 0.f;
+  }
+  __syncthreads();
+  // B fragment of weight m, n-tile nj (output column 8 nj + g), k-step ks
+  auto bfrag = [&](int m, int nj, int ks, uint32_t& b0, uint32_t& b1v) {
+    const __nv_bfloat16* rp = &ws[m][(nj * 8 + g) * kWRow + ks * 16 + 2 * t];
+    b0 = *reinterpret_cast<const uint32_t*>(rp);
+    b1v = *reinterpret_cast<const uint32_t*>(rp + 8);
+  };
+  const long long tiles = (rows + kTileTok - 1) / kTileTok;
+  for (long long tile = static_cast<long long>(blockIdx.x) * 4 + warp; tile < tiles; tile += static_cast<long long>(gridDim.x) * 4) {
+    const long long r0 = tile * kTileTok;
+    const bool okA = r0 + g < rows, okB = r0 + g + 8 < rows;
+    // A fragments of ya (16 x 64 bf16)
+    uint32_t a[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const __nv_bfloat16* pa = ya + (r0 + g) * kEmb + ks * 16 + 2 * t;
+      a[ks][0] = okA ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
+      a[ks][1] = okB ? *reinterpret_cast<const uint32_t*>(pa + 8 * kEmb) : 0u;
+      a[ks][2] = okA ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
+      a[ks][3] = okB ? *reinterpret_cast<const uint32_t*>(pa + 8 * kEmb + 8) : 0u;
+    }
+    // y1 = v + ya wo^T + bo
+    float acc[8][4];
+#pragma unroll
+    for (int nj = 0; nj < 8; ++nj) {
+      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1v;
+        bfrag(0, nj, ks, b0, b1v);
+        mma_bf16(acc[nj], a[ks], b0, b1v);
+      }
+    }
+    float y1[8][4];
+    float sA = 0.f, sB = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 8; ++nj) {
+      const int col = nj * 8 + 2 * t;
+      const float2 bb = *reinterpret_cast<const float2*>(&vec[0][col]);
+      float2 vA = make_float2(0.f, 0.f), vB = make_float2(0.f, 0.f);
+      if (okA) vA = *reinterpret_cast<const float2*>(y + (r0 + g) * kEmb + col);
+      if (okB) vB = *reinterpret_cast<const float2*>(y + (r0 + g + 8) * kEmb + col);
+      y1[nj][0] = vA.x + (acc[nj][0] + bb.x);
+      y1[nj][1] = vA.y + (acc[nj][1] + bb.y);
+      y1[nj][2] = vB.x + (acc[nj][2] + bb.x);
+      y1[nj][3] = vB.y + (acc[nj][3] + bb.y);
+      sA += y1[nj][0] + y1[nj][1];
+      sB += y1[nj][2] + y1[nj][3];
+    }
+    // LayerNorm over the 64 columns of rows g and g + 8 (each spread over the four lanes of a quad)
+    const float mA = quad_sum(sA) * (1.0f / kEmb), mB = quad_sum(sB) * (1.0f / kEmb);
+    float qA = 0.f, qB = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 8; ++nj) {
+      const float d0 = y1[nj][0] - mA, d1 = y1[nj][1] - mA, d2 = y1[nj][2] - mB, d3 = y1[nj][3] - mB;
+      qA += d0 * d0 + d1 * d1;
+      qB += d2 * d2 + d3 * d3;
+    }
+    const float rA = rsqrtf(quad_sum(qA) * (1.0f / kEmb) + eps), rB = rsqrtf(quad_sum(qB) * (1.0f / kEmb) + eps);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nj = 2 * ks + h, col = nj * 8 + 2 * t;
+        const float2 gg = *reinterpret_cast<const float2*>(&vec[1][col]);
+        const float2 be = *reinterpret_cast<const float2*>(&vec[2][col]);
+        a[ks][2 * h] = pack2((y1[nj][0] - mA) * rA * gg.x + be.x, (y1[nj][1] - mA) * rA * gg.y + be.y);
+        a[ks][2 * h + 1] = pack2((y1[nj][2] - mB) * rB * gg.x + be.x, (y1[nj][3] - mB) * rB * gg.y + be.y);
+      }
+    }
+    // h = gelu_tanh(z w1^T + b1)
+#pragma unroll
+    for (int nj = 0; nj < 8; ++nj) {
+      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1v;
+        bfrag(1, nj, ks, b0, b1v);
+        mma_bf16(acc[nj], a[ks], b0, b1v);
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nj = 2 * ks + h, col = nj * 8 + 2 * t;
+        const float2 bb = *reinterpret_cast<const float2*>(&vec[3][col]);
+        float h0 = acc[nj][0] + bb.x, h1 = acc[nj][1] + bb.y, h2 = acc[nj][2] + bb.x, h3 = acc[nj][3] + bb.y;
+        gemm_detail::gelu_tanh_pair(h0, h1);
+        gemm_detail::gelu_tanh_pair(h2, h3);
+        a[ks][2 * h] = pack2(h0, h1);
+        a[ks][2 * h + 1] = pack2(h2, h3);
+      }
+    }
+    // y = y1 + h w2^T + b2
+#pragma unroll
+    for (int nj = 0; nj < 8; ++nj) {
+      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1v;
+        bfrag(2, nj, ks, b0, b1v);
+        mma_bf16(acc[nj], a[ks], b0, b1v);
+      }
+      const int col = nj * 8 + 2 * t;
+      const float2 bb = *reinterpret_cast<const float2*>(&vec[4][col]);
+      if (okA) *reinterpret_cast<float2*>(y + (r0 + g) * kEmb + col) = make_float2(y1[nj][0] + (acc[nj][0] + bb.x), y1[nj][1] + (acc[nj][1] + bb.y));
+      if (okB)
+        *reinterpret_cast<float2*>(y + (r0 + g + 8) * kEmb + col) = make_float2(y1[nj][2] + (acc[nj][2] + bb.x), y1[nj][3] + (acc[nj][3] + bb.y));
+    }
+  }
+}
+
 }  // namespace
 
 template <typename TIN, bool LN>
@@ -524,6 +674,14 @@ extern "C" int evt_performer_workspace_bytes(int B, int T, size_t* out) {
   return EVT_OK;
 }
 
+extern "C" int evt_performer_mlp_fwd(const void* ya, float* y, const void* wo, const float* bo, const float* gamma, const float* beta,
+                                     const void* w1, const float* b1, const void* w2, const float* b2, int64_t rows, float eps,
+                                     evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::performer_mlp_launch(ya, y, wo, bo, gamma, beta, w1, b1, w2, b2, rows, eps, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace,
                                  int B, int T, int emb, int m, float eps, evt_stream stream) {
   int rc = evt_device_check();
@@ -536,6 +694,23 @@ namespace evt {
 size_t performer_workspace_bytes(int B, int T) {
   const size_t nsplit = (T + kChunk - 1) / kChunk;
   return static_cast<size_t>(B) * (nsplit + 1) * (kM + kEmb * kM) * sizeof(float);
+}
+
+int performer_mlp_launch(const void* ya, float* y, const void* wo, const float* bo, const float* gamma, const float* beta, const void* w1,
+                         const float* b1, const void* w2, const float* b2, int64_t rows, float eps, cudaStream_t st) {
+  EVT_CHECK_ARG(ya && y && wo && gamma && beta && w1 && w2, "performer_mlp: null pointer");
+  EVT_CHECK_ARG(rows > 0, "performer_mlp: rows must be positive");
+  for (const void* p : {ya, static_cast<const void*>(y), wo, w1, w2})
+    EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(p) % 16 == 0, "performer_mlp: operands must be 16-byte aligned");
+  const long long tiles = (rows + kTileTok - 1) / kTileTok;
+  const long long want = (tiles + 3) / 4;
+  const long long cap = static_cast<long long>(num_sms()) * 16;  // 4-warp blocks: grid-stride beyond 16 resident blocks per SM
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  performer_mlp_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ya), y, reinterpret_cast<const __nv_bfloat16*>(wo), bo, gamma,
+                                             beta, reinterpret_cast<const __nv_bfloat16*>(w1), b1, reinterpret_cast<const __nv_bfloat16*>(w2),
+                                             b2, rows, eps);
+  EVT_LAUNCH_CHECK("performer_mlp");
+  return EVT_OK;
 }
 
 int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace, int B, int T, int emb,

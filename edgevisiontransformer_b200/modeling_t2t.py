@@ -56,10 +56,8 @@ class _Performer:
         X = ops.unfold_ln_nhwc(x_nhwc, k, s, p, self.g1, self.b1, TF_EPS, ld=self.wkqv.shape[1])
         kqv = ops.linear(X, self.wkqv, self.bkqv, k=self.in_dim)                    # bf16 [B*T, 192]
         yattn, y = ops.performer(kqv, self.w, B, T)                                  # y = v (f32)
-        ops.linear(yattn, self.wo, self.bo, residual=y, out=y, out_dtype=torch.float32)      # y = v + attn_output(.)
-        z = ops.layernorm(y, self.g2, self.b2, TF_EPS)
-        h = ops.linear(z, self.w1, self.bb1, act="gelu_tanh")
-        ops.linear(h, self.w2, self.bb2, residual=y, out=y, out_dtype=torch.float32)         # y += mlp(LN(y))
+        # y = v + attn_output(.) ; y += mlp(LN(y))   (transformer_encoder.py:93-99), one kernel
+        ops.performer_mlp(yattn, y, self.wo, self.bo, self.g2, self.b2, self.w1, self.bb1, self.w2, self.bb2, TF_EPS)
         return y.view(B, oh, ow, 64)
 
 

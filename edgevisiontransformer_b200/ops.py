@@ -308,6 +308,24 @@ def performer(kqv: torch.Tensor, w: torch.Tensor, B: int, T: int, eps: float = 1
     return yattn, vout
 
 
+def performer_mlp(yattn: torch.Tensor, y: torch.Tensor, wo, bo, gamma, beta, w1, b1, w2, b2, eps: float) -> torch.Tensor:
+    """In place on y (f32 [rows, 64], holding v): y += attn_output(yattn); y += fc2(gelu_tanh(fc1(LayerNorm(y)))).
+    yattn bf16 [rows, 64]; wo / w1 / w2 bf16 [64, 64] ([out, in]); one kernel (csrc/performer.cu)."""
+    _need_cuda(yattn, y, wo, bo, gamma, beta, w1, b1, w2, b2)
+    if yattn.dtype != torch.bfloat16 or y.dtype != torch.float32 or yattn.shape != y.shape or y.dim() != 2 or y.shape[1] != 64:
+        raise ValueError("performer_mlp wants yattn bf16 [rows, 64] and y f32 [rows, 64]")
+    if not (yattn.is_contiguous() and y.is_contiguous()):
+        raise ValueError("performer_mlp wants contiguous rows")
+    for w in (wo, w1, w2):
+        if w.dtype != torch.bfloat16 or tuple(w.shape) != (64, 64) or not w.is_contiguous():
+            raise ValueError("performer_mlp: weights must be contiguous bf16 [64, 64]")
+    lib = _lib.load()
+    _lib.check(lib.evt_performer_mlp_fwd(yattn.data_ptr(), y.data_ptr(), wo.data_ptr(), _ptr(bo), gamma.contiguous().data_ptr(),
+                                         beta.contiguous().data_ptr(), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2),
+                                         y.shape[0], float(eps), _stream()), "performer_mlp")
+    return y
+
+
 def set_gemm_pair_mode(mode: int) -> None:
     """-1 automatic, 0 single-CTA GEMM kernel only, 1 CTA-pair (cta_group::2) kernel whenever applicable."""
     _lib.load().evt_gemm_set_pair_mode(int(mode))

@@ -194,6 +194,16 @@ int evt_performer_workspace_bytes(int B, int T, size_t* out);
 int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace,
                       int B, int T, int emb, int m, float eps, evt_stream stream);
 
+/* What Token_performer does after the attention contraction (modeling/layers/transformer_encoder.py:93-99), 64-wide tokens, one
+ * kernel:   y <- y + attn_output(ya) ;  y <- y + fc2(gelu_tanh(fc1(LayerNorm(y))))
+ *   ya : bf16 [rows, 64] (evt_performer_fwd's yattn);  y : f32 [rows, 64], holds v on entry (evt_performer_fwd's vout), in place
+ *   wo, w1, w2 : bf16 [64 out, 64 in] dense;  bo, b1, b2 : f32 [64] or NULL;  gamma, beta : f32 [64] (norm2);  all 16-byte aligned
+ * Same arithmetic as evt_gemm_bias_act (f32 residual) + evt_layernorm_fwd + evt_gemm_bias_act (tanh-GELU) + evt_gemm_bias_act,
+ * which it replaces in the T2T front-end: 640 instead of 1920 bytes of HBM traffic per token. */
+int evt_performer_mlp_fwd(const void* ya, float* y, const void* wo, const float* bo, const float* gamma, const float* beta,
+                          const void* w1, const float* b1, const void* w2, const float* b2, int64_t rows, float eps,
+                          evt_stream stream);
+
 /* ---- Swin shifted-window block (tools.py:265-292 export_onnx_swin, utils.py:14-47 get_swin; arithmetic:
  * SITE/models/swin/modeling_swin.py).  Token rows are kept in the window order of the current block, see
  * edgevisiontransformer_b200/modeling_swin.py. */

@@ -173,6 +173,38 @@ def test_gemm_residual_layernorm_fused(M, N, K):
     assert (xn.float() - want_xn).abs().max().item() < 4e-2
 
 
+@pytest.mark.parametrize("rows", [16, 37, 3136 * 3 + 5])
+def test_performer_tail_in_one_kernel(rows):
+    """evt_performer_mlp_fwd: y = v + attn_output(ya); y += fc2(gelu_tanh(fc1(LN(y)))) for 64-wide tokens -- against fp32 torch on the
+    bf16-rounded operands, and against the four kernels it replaces (same operand roundings: agreement to summation order)."""
+    ops = _ops()
+    ya = _rand((rows, 64), 51).bfloat16()
+    v = _rand((rows, 64), 52) + 0.3 * _rand((rows, 1), 53)
+    wo, w1, w2 = (_rand((64, 64), 54 + i, 0.15).bfloat16() for i in range(3))
+    bo, b1, b2 = (_rand((64,), 57 + i, 0.1) for i in range(3))
+    gamma, beta = 1 + _rand((64,), 60, 0.1), _rand((64,), 61, 0.1)
+    eps = 1e-5
+    canary = torch.full((8, 64), 7.0, device="cuda")
+    buf = torch.cat([v, canary])
+    y = ops.performer_mlp(ya, buf[:rows], wo, bo, gamma, beta, w1, b1, w2, b2, eps)
+    # the four-kernel path
+    y4 = v.clone()
+    ops.linear(ya, wo, bo, residual=y4, out=y4, out_dtype=torch.float32)
+    z = ops.layernorm(y4, gamma, beta, eps)
+    h = ops.linear(z, w1, b1, act="gelu_tanh")
+    ops.linear(h, w2, b2, residual=y4, out=y4, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.equal(buf[rows:], canary)
+    # fp32 reference with the same roundings of the two intermediate operands
+    y1 = v + ya.float() @ wo.float().t() + bo
+    zr = torch.nn.functional.layer_norm(y1, (64,), gamma, beta, eps).bfloat16().float()
+    hr = torch.nn.functional.gelu(zr @ w1.float().t() + b1, approximate="tanh").bfloat16().float()
+    want = y1 + hr @ w2.float().t() + b2
+    assert (y - want).abs().max().item() < 2e-2
+    assert (y - want).abs().mean().item() < 1e-3
+    assert (y - y4).abs().max().item() < 2e-2 and (y - y4).abs().mean().item() < 1e-3
+
+
 @pytest.mark.parametrize("M,N,K,copy_ln", [(256 * 80 + 129, 192, 64, False), (256 * 90 + 1, 192, 230, False), (256 * 75, 384, 384, False),
                                          (256 * 74 + 255, 384, 1536, False), (256 * 80 + 129, 192, 230, True),
                                          (256 * 77 + 33, 384, 1152, True), (197 * 1024, 192, 64, False)])
