@@ -110,9 +110,9 @@ namespace {
 struct Workspace {
   float* resid;
   uint8_t *xn, *qkv, *ctx, *big, *clsn, *hh;  // activations in the GEMM operand type (bf16, or f32 in tf32 mode)
-  // T2T front-end (spec.t2t): per performer stage the unfolded + normalised rows, k|q|v, the attention output, the f32
-  // token stream y and the performer scratch; `pm` = the patch matrix of the embedding GEMM
-  uint8_t *t_x[2], *t_kqv[2], *t_ya[2], *t_ws[2], *t_pm;
+  // T2T front-end (spec.t2t): per performer stage the unfolded + normalised rows, k|q|v, the f32 token
+  // stream y and the performer scratch; `pm` = the patch matrix of the embedding GEMM
+  uint8_t *t_x[2], *t_kqv[2], *t_ws[2], *t_pm;
   float* t_y[2];
   size_t bytes;
 };
@@ -154,9 +154,9 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
     for (int i = 0; i < 2; ++i) {
       const size_t T = static_cast<size_t>(t2t_side(s.image, i)) * t2t_side(s.image, i) * batch;
       const size_t in_ld = i == 0 ? 152 : 576;
-      const size_t ox = take(T * in_ld * 2), ok = take(T * 192 * 2), oa = take(T * 64 * 2), oy = take(T * 64 * 4);
+      const size_t ox = take(T * in_ld * 2), ok = take(T * 192 * 2), oy = take(T * 64 * 4);
       const size_t ow = take(performer_workspace_bytes(batch, t2t_side(s.image, i) * t2t_side(s.image, i)));
-      w.t_x[i] = b + ox, w.t_kqv[i] = b + ok, w.t_ya[i] = b + oa, w.t_y[i] = reinterpret_cast<float*>(b + oy);
+      w.t_x[i] = b + ox, w.t_kqv[i] = b + ok, w.t_y[i] = reinterpret_cast<float*>(b + oy);
       w.t_ws[i] = b + ow;
     }
     w.t_pm = b + take(Mp * 576 * 2);
@@ -436,8 +436,8 @@ extern "C" int evt_model_workspace_bytes(const evt_model* m, int batch, size_t* 
 extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   if (!m) return 0;
   const evt_model_spec& s = m->spec;
-  // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels, the fused attn_output + MLP tail; then the last soft split
-  return (s.t2t ? 2 * 6 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+  // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels (the last one carries attn_output + MLP); then the last soft split
+  return (s.t2t ? 2 * 5 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
 }
 
 static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts* opts, const void* patch_matrix, int64_t patch_ld,
@@ -503,10 +503,18 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
       EVT_STAGE(EVT_STAGE_EMBED, unfold_ln_launch(src, src_dt, w.t_x[i], pw.in_ld, pw.g1, pw.b1, tf_eps, batch, side, side, ch, k, st_, pad_, st));
       EVT_STAGE(EVT_STAGE_EMBED, gemm_launch(w.t_x[i], pw.in_ld, pw.wkqv, pw.in_ld, EVT_BF16, pw.bkqv, nullptr, 0, 0, 0, w.t_kqv[i], EVT_BF16, 192,
                                              0, 0, 0, rows, 192, pw.in_dim, EVT_ACT_NONE, st));
-      EVT_TRY(performer_launch(w.t_kqv[i], 192, pw.w, w.t_ya[i], w.t_y[i], w.t_ws[i], batch, T, 64, 32, 1e-8f, st));
+      // single_attn + attn_output + LayerNorm + MLP (transformer_encoder.py:67-99): the attention contraction's apply kernel carries
+      // each tile through the tail, y = the performer's output rows
+      static const bool two_calls = getenv("EVT_T2T_TWO_CALLS") != nullptr;  // A/B only: performer + tail as separate kernels
+      if (two_calls) {
+        uint8_t* ya = w.t_x[i];  // the unfolded rows are dead once kqv exists: their buffer takes the attention output
+        EVT_TRY(performer_launch(w.t_kqv[i], 192, pw.w, ya, w.t_y[i], w.t_ws[i], batch, T, 64, 32, 1e-8f, st));
+        EVT_TRY(performer_mlp_launch(ya, w.t_y[i], pw.wo, pw.bo, pw.g2, pw.b2, pw.w1, pw.bb1, pw.w2, pw.bb2, rows, tf_eps, st));
+      } else {
+        EVT_TRY(performer_block_launch(w.t_kqv[i], 192, pw.w, w.t_y[i], w.t_ws[i], batch, T, 1e-8f, pw.wo, pw.bo, pw.g2, pw.b2, pw.w1,
+                                       pw.bb1, pw.w2, pw.bb2, tf_eps, st));
+      }
       EVT_TRY(mark(EVT_STAGE_EMBED));
-      // y = v + attn_output(.) ; y += mlp(LN(y))   (transformer_encoder.py:93-99): one kernel, 64-wide rows never leave the SM
-      EVT_STAGE(EVT_STAGE_EMBED, performer_mlp_launch(w.t_ya[i], w.t_y[i], pw.wo, pw.bo, pw.g2, pw.b2, pw.w1, pw.bb1, pw.w2, pw.bb2, rows, tf_eps, st));
       src = w.t_y[i], src_dt = EVT_F32, side = so, ch = 64;
     }
     EVT_STAGE(EVT_STAGE_EMBED, unfold_ln_launch(src, src_dt, w.t_pm, 576, nullptr, nullptr, tf_eps, batch, side, side, 64, 3, 2, 1, st));

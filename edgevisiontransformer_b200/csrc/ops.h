@@ -57,6 +57,10 @@ int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, f
 // entry; wo / w1 / w2 bf16 [64 out, 64 in] dense; tanh-GELU
 int performer_mlp_launch(const void* ya, float* y, const void* wo, const float* bo, const float* gamma, const float* beta, const void* w1,
                          const float* b1, const void* w2, const float* b2, int64_t rows, float eps, cudaStream_t st);
+// the whole Token_performer after the kqv projection in three launches: y f32 [B*T, 64] = the performer's output rows
+int performer_block_launch(const void* kqv, int64_t ld, const float* w, float* y, void* workspace, int B, int T, float eps, const void* wo,
+                           const float* bo, const float* gamma, const float* beta, const void* w1, const float* b1, const void* w2,
+                           const float* b2, float ln_eps, cudaStream_t st);
 int unfold_launch(const void* x, int x_dtype, void* out, int64_t ldo, int B, int H, int W, int C, int k, int s, int p,
                   cudaStream_t st);
 

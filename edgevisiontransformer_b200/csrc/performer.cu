@@ -370,12 +370,149 @@ __global__ void __launch_bounds__(256) performer_reduce_final_kernel(const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------- performer tail
+// Everything the Token_performer does after the attention contraction (modeling/layers/transformer_encoder.py:93-99), for 64-wide
+// tokens, in ONE pass over the rows:
+//     y  = v + attn_output(ya)            (Dense 64 -> 64; v = the f32 copy of the value rows the apply kernel wrote)
+//     y += mlp(LayerNorm(y))              (Dense 64 -> 64, tanh-GELU, Dense 64 -> 64)
+// Before: GEMM (f32 reduce-add), LayerNorm kernel, GEMM + GELU, GEMM (reduce-add) -- four launches moving 1920 bytes per token;
+// here 640 (ya in, y in, y out).  Per 16-token tile a warp chains three m16n8k16 products whose accumulator fragments are the
+// next product's A fragments (two adjacent n-tiles = one k-step), the LayerNorm statistics are quad reductions over the
+// accumulator fragment (f32, centred variance), the three 64 x 64 weights sit in shared memory with rows padded to 144 bytes
+// (conflict-free B-fragment loads).  Same arithmetic as the four kernels (bf16 operands, f32 accumulation, f32 skip), so the
+// results agree with them to summation order.
+constexpr int kWRow = 72;  // bf16 elements per padded weight row
+
+struct TailWeights {
+  const __nv_bfloat16 *wo, *w1, *w2;   // [64 out, 64 in] dense
+  const float *bo, *gamma, *beta, *b1, *b2;
+  float eps;
+};
+struct TailSmem {
+  __align__(16) __nv_bfloat16 ws[3][kEmb * kWRow];
+  __align__(16) float vec[5][kEmb];  // bo, gamma, beta, b1, b2
+};
+
+// cooperative load by the whole block (128 threads); the caller synchronises afterwards
+__device__ __forceinline__ void tail_load(TailSmem& sm, const TailWeights& w) {
+  for (int i = threadIdx.x; i < 3 * kEmb * 8; i += blockDim.x) {  // 16-byte pieces: 8 per 64-element row
+    const int m = i / (kEmb * 8), r = (i / 8) % kEmb, c = i % 8;
+    const __nv_bfloat16* src = m == 0 ? w.wo : m == 1 ? w.w1 : w.w2;
+    *reinterpret_cast<uint4*>(&sm.ws[m][r * kWRow + c * 8]) = *reinterpret_cast<const uint4*>(src + r * kEmb + c * 8);
+  }
+  for (int i = threadIdx.x; i < 5 * kEmb; i += blockDim.x) {
+    const int m = i / kEmb, c = i % kEmb;
+    const float* src = m == 0 ? w.bo : m == 1 ? w.gamma : m == 2 ? w.beta : m == 3 ? w.b1 : w.b2;
+    sm.vec[m][c] = src != nullptr ? src[c] : 0.f;
+  }
+}
+
+// One 16-token tile.  a: A fragments of ya (bf16, 4 k-steps); y1: on entry v in accumulator-fragment layout (rows g / g + 8,
+// columns 8 nj + 2t, + 1), on exit the performer's output rows.
+__device__ __forceinline__ void tail_tile(const TailSmem& sm, uint32_t (&a)[4][4], float (&y1)[8][4], int g, int t, float eps) {
+  auto bfrag = [&](int m, int nj, int ks, uint32_t& b0, uint32_t& b1v) {
+    const __nv_bfloat16* rp = &sm.ws[m][(nj * 8 + g) * kWRow + ks * 16 + 2 * t];
+    b0 = *reinterpret_cast<const uint32_t*>(rp);
+    b1v = *reinterpret_cast<const uint32_t*>(rp + 8);
+  };
+  float acc[8][4];
+  // y1 = v + ya wo^T + bo
+  float sA = 0.f, sB = 0.f;
+#pragma unroll
+  for (int nj = 0; nj < 8; ++nj) {
+    acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t b0, b1v;
+      bfrag(0, nj, ks, b0, b1v);
+      mma_bf16(acc[nj], a[ks], b0, b1v);
+    }
+    const float2 bb = *reinterpret_cast<const float2*>(&sm.vec[0][nj * 8 + 2 * t]);
+    y1[nj][0] += acc[nj][0] + bb.x;
+    y1[nj][1] += acc[nj][1] + bb.y;
+    y1[nj][2] += acc[nj][2] + bb.x;
+    y1[nj][3] += acc[nj][3] + bb.y;
+    sA += y1[nj][0] + y1[nj][1];
+    sB += y1[nj][2] + y1[nj][3];
+  }
+  // LayerNorm over the 64 columns of rows g and g + 8 (each spread over the four lanes of a quad)
+  const float mA = quad_sum(sA) * (1.0f / kEmb), mB = quad_sum(sB) * (1.0f / kEmb);
+  float qA = 0.f, qB = 0.f;
+#pragma unroll
+  for (int nj = 0; nj < 8; ++nj) {
+    const float d0 = y1[nj][0] - mA, d1 = y1[nj][1] - mA, d2 = y1[nj][2] - mB, d3 = y1[nj][3] - mB;
+    qA += d0 * d0 + d1 * d1;
+    qB += d2 * d2 + d3 * d3;
+  }
+  const float rA = rsqrtf(quad_sum(qA) * (1.0f / kEmb) + eps), rB = rsqrtf(quad_sum(qB) * (1.0f / kEmb) + eps);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nj = 2 * ks + h, col = nj * 8 + 2 * t;
+      const float2 gg = *reinterpret_cast<const float2*>(&sm.vec[1][col]);
+      const float2 be = *reinterpret_cast<const float2*>(&sm.vec[2][col]);
+      a[ks][2 * h] = pack2((y1[nj][0] - mA) * rA * gg.x + be.x, (y1[nj][1] - mA) * rA * gg.y + be.y);
+      a[ks][2 * h + 1] = pack2((y1[nj][2] - mB) * rB * gg.x + be.x, (y1[nj][3] - mB) * rB * gg.y + be.y);
+    }
+  }
+  // h = gelu_tanh(z w1^T + b1)
+#pragma unroll
+  for (int nj = 0; nj < 8; ++nj) {
+    acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t b0, b1v;
+      bfrag(1, nj, ks, b0, b1v);
+      mma_bf16(acc[nj], a[ks], b0, b1v);
+    }
+  }
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nj = 2 * ks + h;
+      const float2 bb = *reinterpret_cast<const float2*>(&sm.vec[3][nj * 8 + 2 * t]);
+      float h0 = acc[nj][0] + bb.x, h1 = acc[nj][1] + bb.y, h2 = acc[nj][2] + bb.x, h3 = acc[nj][3] + bb.y;
+      gemm_detail::gelu_tanh_pair(h0, h1);
+      gemm_detail::gelu_tanh_pair(h2, h3);
+      a[ks][2 * h] = pack2(h0, h1);
+      a[ks][2 * h + 1] = pack2(h2, h3);
+    }
+  }
+  // y = y1 + h w2^T + b2
+#pragma unroll
+  for (int nj = 0; nj < 8; ++nj) {
+    acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t b0, b1v;
+      bfrag(2, nj, ks, b0, b1v);
+      mma_bf16(acc[nj], a[ks], b0, b1v);
+    }
+    const float2 bb = *reinterpret_cast<const float2*>(&sm.vec[4][nj * 8 + 2 * t]);
+    y1[nj][0] += acc[nj][0] + bb.x;
+    y1[nj][1] += acc[nj][1] + bb.y;
+    y1[nj][2] += acc[nj][2] + bb.x;
+    y1[nj][3] += acc[nj][3] + bb.y;
+  }
+}
+
 // per token: yattn (bf16 [B*T, 64]) = (qp kptv^T)/(qp.ksum + eps);  vout (f32 [B*T, 64]) = v (the skip connection that
 // the attn_output GEMM then reduce-adds into, transformer_encoder.py:93).
+// TAIL: the tile goes straight on through attn_output + LayerNorm + MLP (tail_tile above) -- ya and v never leave the registers,
+// vout receives the performer's finished output rows and yattn is not written: 512 bytes of HBM traffic per token (q, v in; y out)
+// instead of 640 here + 640 in the tail kernel.  Bit-identical to the two kernels (same roundings, same order).
+template <bool TAIL>
 __global__ void __launch_bounds__(128) performer_apply_kernel(const __nv_bfloat16* __restrict__ kqv, long long ld,
                                                               const float* __restrict__ w, const float* __restrict__ stats,
                                                               __nv_bfloat16* __restrict__ yattn, float* __restrict__ vout,
-                                                              int T, float eps) {
+                                                              int T, float eps, const TailWeights tw) {
+  __shared__ TailSmem sm_tail[1];  // unused (and eliminated) without TAIL
+  if (TAIL) {
+    tail_load(sm_tail[0], tw);
+    __syncthreads();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.y;
@@ -446,72 +583,64 @@ __global__ void __launch_bounds__(128) performer_apply_kernel(const __nv_bfloat1
       pa[nf >> 1][(nf & 1) * 2 + 1] = pack2(p2, p3);
     }
     const float invA = 1.0f / (quad_sum(dA) + eps), invB = 1.0f / (quad_sum(dB) + eps);
+    uint32_t ya_frag[4][4];  // TAIL: yattn as the A fragments of the attn_output product (n-tiles 2 ks, 2 ks + 1 = k-step ks)
 #pragma unroll
     for (int ne = 0; ne < 8; ++ne) {
       float y[4] = {0.f, 0.f, 0.f, 0.f};
       mma_bf16(y, pa[0], kvb[ne][0][0], kvb[ne][0][1]);
       mma_bf16(y, pa[1], kvb[ne][1][0], kvb[ne][1][1]);
       const int col = ne * 8 + 2 * t;
-      if (okA) *reinterpret_cast<uint32_t*>(yattn + (r0 + g) * kEmb + col) = pack2(y[0] * invA, y[1] * invA);
-      if (okB) *reinterpret_cast<uint32_t*>(yattn + (r0 + g + 8) * kEmb + col) = pack2(y[2] * invB, y[3] * invB);
+      if (TAIL) {
+        ya_frag[ne >> 1][(ne & 1) * 2] = pack2(y[0] * invA, y[1] * invA);
+        ya_frag[ne >> 1][(ne & 1) * 2 + 1] = pack2(y[2] * invB, y[3] * invB);
+      } else {
+        if (okA) *reinterpret_cast<uint32_t*>(yattn + (r0 + g) * kEmb + col) = pack2(y[0] * invA, y[1] * invA);
+        if (okB) *reinterpret_cast<uint32_t*>(yattn + (r0 + g + 8) * kEmb + col) = pack2(y[2] * invB, y[3] * invB);
+      }
     }
-    // vout = v as f32: 16 rows x 32 bf16 pairs, coalesced
+    if (TAIL) {
+      float y1[8][4];  // v in accumulator-fragment layout
 #pragma unroll
-    for (int i = 0; i < kTileTok; ++i) {
-      if (tb + i < t1) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + i * ld + 128 + 2 * lane));
-        *reinterpret_cast<float2*>(vout + (r0 + i) * kEmb + 2 * lane) = f;
+      for (int nj = 0; nj < 8; ++nj) {
+        const int col = 128 + nj * 8 + 2 * t;
+        float2 vA = make_float2(0.f, 0.f), vB = make_float2(0.f, 0.f);
+        if (okA) vA = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + g * ld + col));
+        if (okB) vB = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (g + 8) * ld + col));
+        y1[nj][0] = vA.x, y1[nj][1] = vA.y, y1[nj][2] = vB.x, y1[nj][3] = vB.y;
+      }
+      tail_tile(sm_tail[0], ya_frag, y1, g, t, tw.eps);
+#pragma unroll
+      for (int nj = 0; nj < 8; ++nj) {
+        const int col = nj * 8 + 2 * t;
+        if (okA) *reinterpret_cast<float2*>(vout + (r0 + g) * kEmb + col) = make_float2(y1[nj][0], y1[nj][1]);
+        if (okB) *reinterpret_cast<float2*>(vout + (r0 + g + 8) * kEmb + col) = make_float2(y1[nj][2], y1[nj][3]);
+      }
+    } else {
+      // vout = v as f32: 16 rows x 32 bf16 pairs, coalesced
+#pragma unroll
+      for (int i = 0; i < kTileTok; ++i) {
+        if (tb + i < t1) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + i * ld + 128 + 2 * lane));
+          *reinterpret_cast<float2*>(vout + (r0 + i) * kEmb + 2 * lane) = f;
+        }
       }
     }
   }
 }
 
 
-// ---------------------------------------------------------------------------------------------- performer tail
-// Everything the Token_performer does after the attention contraction (modeling/layers/transformer_encoder.py:93-99), for 64-wide
-// tokens, in ONE pass over the rows:
-//     y  = v + attn_output(ya)            (Dense 64 -> 64; v = the f32 copy of the value rows the apply kernel wrote)
-//     y += mlp(LayerNorm(y))              (Dense 64 -> 64, tanh-GELU, Dense 64 -> 64)
-// Before: GEMM (f32 reduce-add), LayerNorm kernel, GEMM + GELU, GEMM (reduce-add) -- four launches moving 1920 bytes per token;
-// here 640 (ya in, y in, y out).  Per 16-token tile a warp chains three m16n8k16 products whose accumulator fragments are the
-// next product's A fragments (two adjacent n-tiles = one k-step), the LayerNorm statistics are quad reductions over the
-// accumulator fragment (f32, centred variance), the three 64 x 64 weights sit in shared memory with rows padded to 144 bytes
-// (conflict-free B-fragment loads).  Same arithmetic as the four kernels (bf16 operands, f32 accumulation, f32 skip), so the
-// results agree with them to summation order.
-constexpr int kWRow = 72;  // bf16 elements per padded weight row
 
-__global__ void __launch_bounds__(128) performer_mlp_kernel(const __nv_bfloat16* __restrict__ ya, float* __restrict__ y,
-                                                            const __nv_bfloat16* __restrict__ wo, const float* __restrict__ bo,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const __nv_bfloat16* __restrict__ w1, const float* __restrict__ b1,
-                                                            const __nv_bfloat16* __restrict__ w2, const float* __restrict__ b2,
-                                                            long long rows, float eps) {
-  __shared__ __align__(16) __nv_bfloat16 ws[3][kEmb * kWRow];
-  __shared__ __align__(16) float vec[5][kEmb];  // bo, gamma, beta, b1, b2
+__global__ void __launch_bounds__(128) performer_mlp_kernel(const __nv_bfloat16* __restrict__ ya, float* __restrict__ y, const TailWeights tw,
+                                                            long long rows) {
+  __shared__ TailSmem sm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = threadIdx.x; i < 3 * kEmb * 8; i += 128) {  // 16-byte pieces: 8 per 64-element row
-    const int m = i / (kEmb * 8), r = (i / 8) % kEmb, c = i % 8;
-    const __nv_bfloat16* src = m == 0 ? wo : m == 1 ? w1 : w2;
-    *reinterpret_cast<uint4*>(&ws[m][r * kWRow + c * 8]) = *reinterpret_cast<const uint4*>(src + r * kEmb + c * 8);
-  }
-  for (int i = threadIdx.x; i < 5 * kEmb; i += 128) {
-    const int m = i / kEmb, c = i % kEmb;
-    const float* src = m == 0 ? bo : m == 1 ? gamma : m == 2 ? beta : m == 3 ? b1 : b2;
-    vec[m][c] = src != nullptr ? src[c] : 0.f;
-  }
+  tail_load(sm, tw);
   __syncthreads();
-  // B fragment of weight m, n-tile nj (output column 8 nj + g), k-step ks
-  auto bfrag = [&](int m, int nj, int ks, uint32_t& b0, uint32_t& b1v) {
-    const __nv_bfloat16* rp = &ws[m][(nj * 8 + g) * kWRow + ks * 16 + 2 * t];
-    b0 = *reinterpret_cast<const uint32_t*>(rp);
-    b1v = *reinterpret_cast<const uint32_t*>(rp + 8);
-  };
   const long long tiles = (rows + kTileTok - 1) / kTileTok;
   for (long long tile = static_cast<long long>(blockIdx.x) * 4 + warp; tile < tiles; tile += static_cast<long long>(gridDim.x) * 4) {
     const long long r0 = tile * kTileTok;
     const bool okA = r0 + g < rows, okB = r0 + g + 8 < rows;
-    // A fragments of ya (16 x 64 bf16)
     uint32_t a[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -521,94 +650,21 @@ __global__ void __launch_bounds__(128) performer_mlp_kernel(const __nv_bfloat16*
       a[ks][2] = okA ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
       a[ks][3] = okB ? *reinterpret_cast<const uint32_t*>(pa + 8 * kEmb + 8) : 0u;
     }
-    // y1 = v + ya wo^T + bo
-    float acc[8][4];
-#pragma unroll
-    for (int nj = 0; nj < 8; ++nj) {
-      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1v;
-        bfrag(0, nj, ks, b0, b1v);
-        mma_bf16(acc[nj], a[ks], b0, b1v);
-      }
-    }
     float y1[8][4];
-    float sA = 0.f, sB = 0.f;
 #pragma unroll
     for (int nj = 0; nj < 8; ++nj) {
       const int col = nj * 8 + 2 * t;
-      const float2 bb = *reinterpret_cast<const float2*>(&vec[0][col]);
       float2 vA = make_float2(0.f, 0.f), vB = make_float2(0.f, 0.f);
       if (okA) vA = *reinterpret_cast<const float2*>(y + (r0 + g) * kEmb + col);
       if (okB) vB = *reinterpret_cast<const float2*>(y + (r0 + g + 8) * kEmb + col);
-      y1[nj][0] = vA.x + (acc[nj][0] + bb.x);
-      y1[nj][1] = vA.y + (acc[nj][1] + bb.y);
-      y1[nj][2] = vB.x + (acc[nj][2] + bb.x);
-      y1[nj][3] = vB.y + (acc[nj][3] + bb.y);
-      sA += y1[nj][0] + y1[nj][1];
-      sB += y1[nj][2] + y1[nj][3];
+      y1[nj][0] = vA.x, y1[nj][1] = vA.y, y1[nj][2] = vB.x, y1[nj][3] = vB.y;
     }
-    // LayerNorm over the 64 columns of rows g and g + 8 (each spread over the four lanes of a quad)
-    const float mA = quad_sum(sA) * (1.0f / kEmb), mB = quad_sum(sB) * (1.0f / kEmb);
-    float qA = 0.f, qB = 0.f;
+    tail_tile(sm, a, y1, g, t, tw.eps);
 #pragma unroll
     for (int nj = 0; nj < 8; ++nj) {
-      const float d0 = y1[nj][0] - mA, d1 = y1[nj][1] - mA, d2 = y1[nj][2] - mB, d3 = y1[nj][3] - mB;
-      qA += d0 * d0 + d1 * d1;
-      qB += d2 * d2 + d3 * d3;
-    }
-    const float rA = rsqrtf(quad_sum(qA) * (1.0f / kEmb) + eps), rB = rsqrtf(quad_sum(qB) * (1.0f / kEmb) + eps);
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nj = 2 * ks + h, col = nj * 8 + 2 * t;
-        const float2 gg = *reinterpret_cast<const float2*>(&vec[1][col]);
-        const float2 be = *reinterpret_cast<const float2*>(&vec[2][col]);
-        a[ks][2 * h] = pack2((y1[nj][0] - mA) * rA * gg.x + be.x, (y1[nj][1] - mA) * rA * gg.y + be.y);
-        a[ks][2 * h + 1] = pack2((y1[nj][2] - mB) * rB * gg.x + be.x, (y1[nj][3] - mB) * rB * gg.y + be.y);
-      }
-    }
-    // h = gelu_tanh(z w1^T + b1)
-#pragma unroll
-    for (int nj = 0; nj < 8; ++nj) {
-      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1v;
-        bfrag(1, nj, ks, b0, b1v);
-        mma_bf16(acc[nj], a[ks], b0, b1v);
-      }
-    }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nj = 2 * ks + h, col = nj * 8 + 2 * t;
-        const float2 bb = *reinterpret_cast<const float2*>(&vec[3][col]);
-        float h0 = acc[nj][0] + bb.x, h1 = acc[nj][1] + bb.y, h2 = acc[nj][2] + bb.x, h3 = acc[nj][3] + bb.y;
-        gemm_detail::gelu_tanh_pair(h0, h1);
-        gemm_detail::gelu_tanh_pair(h2, h3);
-        a[ks][2 * h] = pack2(h0, h1);
-        a[ks][2 * h + 1] = pack2(h2, h3);
-      }
-    }
-    // y = y1 + h w2^T + b2
-#pragma unroll
-    for (int nj = 0; nj < 8; ++nj) {
-      acc[nj][0] = acc[nj][1] = acc[nj][2] = acc[nj][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1v;
-        bfrag(2, nj, ks, b0, b1v);
-        mma_bf16(acc[nj], a[ks], b0, b1v);
-      }
       const int col = nj * 8 + 2 * t;
-      const float2 bb = *reinterpret_cast<const float2*>(&vec[4][col]);
-      if (okA) *reinterpret_cast<float2*>(y + (r0 + g) * kEmb + col) = make_float2(y1[nj][0] + (acc[nj][0] + bb.x), y1[nj][1] + (acc[nj][1] + bb.y));
-      if (okB)
-        *reinterpret_cast<float2*>(y + (r0 + g + 8) * kEmb + col) = make_float2(y1[nj][2] + (acc[nj][2] + bb.x), y1[nj][3] + (acc[nj][3] + bb.y));
+      if (okA) *reinterpret_cast<float2*>(y + (r0 + g) * kEmb + col) = make_float2(y1[nj][0], y1[nj][1]);
+      if (okB) *reinterpret_cast<float2*>(y + (r0 + g + 8) * kEmb + col) = make_float2(y1[nj][2], y1[nj][3]);
     }
   }
 }
@@ -682,6 +738,15 @@ extern "C" int evt_performer_mlp_fwd(const void* ya, float* y, const void* wo, c
   return evt::performer_mlp_launch(ya, y, wo, bo, gamma, beta, w1, b1, w2, b2, rows, eps, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int evt_performer_block_fwd(const void* kqv, int64_t ld, const float* w, float* y, void* workspace, int B, int T, float eps,
+                                       const void* wo, const float* bo, const float* gamma, const float* beta, const void* w1,
+                                       const float* b1, const void* w2, const float* b2, float ln_eps, evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  return evt::performer_block_launch(kqv, ld, w, y, workspace, B, T, eps, wo, bo, gamma, beta, w1, b1, w2, b2, ln_eps,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int evt_performer_fwd(const void* kqv, int64_t ld, const float* w, void* yattn, float* vout, void* workspace,
                                  int B, int T, int emb, int m, float eps, evt_stream stream) {
   int rc = evt_device_check();
@@ -706,9 +771,10 @@ int performer_mlp_launch(const void* ya, float* y, const void* wo, const float* 
   const long long want = (tiles + 3) / 4;
   const long long cap = static_cast<long long>(num_sms()) * 16;  // 4-warp blocks: grid-stride beyond 16 resident blocks per SM
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  performer_mlp_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ya), y, reinterpret_cast<const __nv_bfloat16*>(wo), bo, gamma,
-                                             beta, reinterpret_cast<const __nv_bfloat16*>(w1), b1, reinterpret_cast<const __nv_bfloat16*>(w2),
-                                             b2, rows, eps);
+  TailWeights tw;
+  tw.wo = reinterpret_cast<const __nv_bfloat16*>(wo), tw.w1 = reinterpret_cast<const __nv_bfloat16*>(w1), tw.w2 = reinterpret_cast<const __nv_bfloat16*>(w2);
+  tw.bo = bo, tw.gamma = gamma, tw.beta = beta, tw.b1 = b1, tw.b2 = b2, tw.eps = eps;
+  performer_mlp_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ya), y, tw, rows);
   EVT_LAUNCH_CHECK("performer_mlp");
   return EVT_OK;
 }
@@ -731,9 +797,35 @@ int performer_launch(const void* kqv, int64_t ld, const float* w, void* yattn, f
   EVT_LAUNCH_CHECK("performer_reduce");
   performer_reduce_final_kernel<<<B, 256, 0, st>>>(partial, stats, nsplit);
   EVT_LAUNCH_CHECK("performer_reduce_final");
-  performer_apply_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(kqv), ld, w, stats,
-                                               reinterpret_cast<__nv_bfloat16*>(yattn), vout, T, eps);
+  performer_apply_kernel<false><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(kqv), ld, w, stats,
+                                                      reinterpret_cast<__nv_bfloat16*>(yattn), vout, T, eps, TailWeights{});
   EVT_LAUNCH_CHECK("performer_apply");
+  return EVT_OK;
+}
+
+// The whole Token_performer after the kqv projection: attention contraction + attn_output + LayerNorm + MLP; y f32 [B*T, 64]
+int performer_block_launch(const void* kqv, int64_t ld, const float* w, float* y, void* workspace, int B, int T, float eps, const void* wo,
+                           const float* bo, const float* gamma, const float* beta, const void* w1, const float* b1, const void* w2,
+                           const float* b2, float ln_eps, cudaStream_t st) {
+  EVT_CHECK_ARG(kqv && w && y && workspace && wo && gamma && beta && w1 && w2, "performer_block: null pointer");
+  EVT_CHECK_ARG(B > 0 && T > 0 && B <= 65535, "performer_block: B in 1..65535 and T > 0");
+  EVT_CHECK_ARG(ld >= 3 * kEmb && ld % 8 == 0 && reinterpret_cast<uintptr_t>(kqv) % 16 == 0,
+                "performer_block: kqv rows must be 16-byte aligned with a leading dimension >= 192");
+  for (const void* p : {static_cast<const void*>(w), static_cast<const void*>(workspace), static_cast<const void*>(y), wo, w1, w2})
+    EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(p) % 16 == 0, "performer_block: operands must be 16-byte aligned");
+  const int nsplit = (T + kChunk - 1) / kChunk;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* stats = partial + static_cast<size_t>(B) * nsplit * (kM + kEmb * kM);
+  dim3 grid(nsplit, B);
+  performer_reduce_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(kqv), ld, w, partial, T, nsplit);
+  EVT_LAUNCH_CHECK("performer_reduce");
+  performer_reduce_final_kernel<<<B, 256, 0, st>>>(partial, stats, nsplit);
+  EVT_LAUNCH_CHECK("performer_reduce_final");
+  TailWeights tw;
+  tw.wo = reinterpret_cast<const __nv_bfloat16*>(wo), tw.w1 = reinterpret_cast<const __nv_bfloat16*>(w1), tw.w2 = reinterpret_cast<const __nv_bfloat16*>(w2);
+  tw.bo = bo, tw.gamma = gamma, tw.beta = beta, tw.b1 = b1, tw.b2 = b2, tw.eps = ln_eps;
+  performer_apply_kernel<true><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(kqv), ld, w, stats, nullptr, y, T, eps, tw);
+  EVT_LAUNCH_CHECK("performer_apply_tail");
   return EVT_OK;
 }
 

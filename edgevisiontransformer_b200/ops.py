@@ -326,6 +326,30 @@ def performer_mlp(yattn: torch.Tensor, y: torch.Tensor, wo, bo, gamma, beta, w1,
     return y
 
 
+def performer_block(kqv: torch.Tensor, w: torch.Tensor, B: int, T: int, wo, bo, gamma, beta, w1, b1, w2, b2, ln_eps: float,
+                    eps: float = 1e-8) -> torch.Tensor:
+    """performer() followed by performer_mlp() in three launches (the apply kernel carries each tile through the tail):
+    kqv bf16 [B*T, >=192] -> y f32 [B*T, 64].  Bit-identical to the two calls."""
+    _need_cuda(kqv, w, wo, bo, gamma, beta, w1, b1, w2, b2)
+    if kqv.dtype != torch.bfloat16 or kqv.dim() != 2 or kqv.shape[0] != B * T or kqv.stride(1) != 1:
+        raise ValueError("performer_block wants a bf16 [B*T, 192] kqv matrix")
+    if tuple(w.shape) != (32, 64) or w.dtype != torch.float32:
+        raise ValueError("performer_block: w must be f32 [32, 64]")
+    for m in (wo, w1, w2):
+        if m.dtype != torch.bfloat16 or tuple(m.shape) != (64, 64) or not m.is_contiguous():
+            raise ValueError("performer_block: weights must be contiguous bf16 [64, 64]")
+    import ctypes as C
+    lib = _lib.load()
+    n = C.c_size_t()
+    _lib.check(lib.evt_performer_workspace_bytes(B, T, C.byref(n)), "performer_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=kqv.device)
+    y = torch.empty((B * T, 64), dtype=torch.float32, device=kqv.device)
+    _lib.check(lib.evt_performer_block_fwd(kqv.data_ptr(), kqv.stride(0), w.contiguous().data_ptr(), y.data_ptr(), ws.data_ptr(), B, T,
+                                           float(eps), wo.data_ptr(), _ptr(bo), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                           w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), float(ln_eps), _stream()), "performer_block")
+    return y
+
+
 def set_gemm_pair_mode(mode: int) -> None:
     """-1 automatic, 0 single-CTA GEMM kernel only, 1 CTA-pair (cta_group::2) kernel whenever applicable."""
     _lib.load().evt_gemm_set_pair_mode(int(mode))

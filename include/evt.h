@@ -204,6 +204,13 @@ int evt_performer_mlp_fwd(const void* ya, float* y, const void* wo, const float*
                           const void* w1, const float* b1, const void* w2, const float* b2, int64_t rows, float eps,
                           evt_stream stream);
 
+/* evt_performer_fwd + evt_performer_mlp_fwd in three launches instead of four: the apply kernel carries each 16-token tile straight
+ * on through attn_output + LayerNorm + MLP, so yattn and v never go to HBM (512 bytes per token: q, v in; y out).  Bit-identical to
+ * the two calls.  y : f32 [B*T, 64] out = the Token_performer's output rows; ln_eps = norm2's epsilon. */
+int evt_performer_block_fwd(const void* kqv, int64_t ld, const float* w, float* y, void* workspace, int B, int T, float eps,
+                            const void* wo, const float* bo, const float* gamma, const float* beta, const void* w1,
+                            const float* b1, const void* w2, const float* b2, float ln_eps, evt_stream stream);
+
 /* ---- Swin shifted-window block (tools.py:265-292 export_onnx_swin, utils.py:14-47 get_swin; arithmetic:
  * SITE/models/swin/modeling_swin.py).  Token rows are kept in the window order of the current block, see
  * edgevisiontransformer_b200/modeling_swin.py. */

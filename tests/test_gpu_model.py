@@ -176,7 +176,7 @@ def test_t2t_front_end_and_model():
         assert torch.equal(m(x.cuda()).logits, m.core.forward_embedded(m.tokens(x.cuda())).logits)
     finally:
         ops.set_gemm_split_k(True)
-    assert m.launches_per_forward() == 13 + 2 + 7 * 3 + 2     # front-end: 2 x (unfold+LN, kqv, 3 performer, tail) + last split
+    assert m.launches_per_forward() == 11 + 2 + 7 * 3 + 2     # front-end: 2 x (unfold+LN, kqv, 3 performer kernels) + last split
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 224, 224, device="cuda"))
     for _ in range(2):                                   # latency path: one CUDA graph over front-end + encoder

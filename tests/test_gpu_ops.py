@@ -205,6 +205,23 @@ def test_performer_tail_in_one_kernel(rows):
     assert (y - y4).abs().max().item() < 2e-2 and (y - y4).abs().mean().item() < 1e-3
 
 
+@pytest.mark.parametrize("B,T", [(2, 784), (3, 100), (1, 3136)])
+def test_performer_block_equals_its_two_halves(B, T):
+    """evt_performer_block_fwd (the apply kernel carries each tile through attn_output + LayerNorm + MLP) is bit-identical to
+    evt_performer_fwd followed by evt_performer_mlp_fwd; T = 100 leaves a partial 16-token tile and a partial 256-token chunk."""
+    ops = _ops()
+    kqv = _rand((B * T, 192), 71, 0.5).bfloat16()
+    w = _rand((32, 64), 72) * math.sqrt(32) / 8
+    wo, w1, w2 = (_rand((64, 64), 73 + i, 0.15).bfloat16() for i in range(3))
+    bo, b1, b2 = (_rand((64,), 76 + i, 0.1) for i in range(3))
+    gamma, beta = 1 + _rand((64,), 79, 0.1), _rand((64,), 80, 0.1)
+    ya, v = ops.performer(kqv, w, B, T)
+    two = ops.performer_mlp(ya, v, wo, bo, gamma, beta, w1, b1, w2, b2, 1e-5)
+    one = ops.performer_block(kqv, w, B, T, wo, bo, gamma, beta, w1, b1, w2, b2, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(one).all() and torch.equal(one, two)
+
+
 @pytest.mark.parametrize("M,N,K,copy_ln", [(256 * 80 + 129, 192, 64, False), (256 * 90 + 1, 192, 230, False), (256 * 75, 384, 384, False),
                                          (256 * 74 + 255, 384, 1536, False), (256 * 80 + 129, 192, 230, True),
                                          (256 * 77 + 33, 384, 1152, True), (197 * 1024, 192, 64, False)])
