@@ -84,7 +84,7 @@ def build_model(name: str, precision: str = "bf16", max_batch: int = 512, device
         from ..modeling_t2t import B200T2TViT
         hidden, depth, heads, ratio = T2T[name]
         m = B200T2TViT(_random_t2t_weights(hidden, depth, heads, ratio), depth=depth, num_heads=heads, device=device,
-                       max_batch=min(max_batch, 256), precision=precision)
+                       max_batch=min(max_batch, 1024), precision=precision)
         return m, (224, 224, 3), f"{name} random-init ({precision}), NHWC input"
     if name in SWIN:
         from transformers import SwinConfig, SwinForImageClassification
@@ -93,7 +93,7 @@ def build_model(name: str, precision: str = "bf16", max_batch: int = 512, device
         torch.manual_seed(0)
         hf = SwinForImageClassification(SwinConfig(image_size=224, patch_size=4, window_size=7, embed_dim=dim, depths=depths,
                                                    num_heads=heads, num_labels=1000)).eval()
-        m = B200SwinForImageClassification.from_hf(hf, device=device, max_batch=min(max_batch, 256))
+        m = B200SwinForImageClassification.from_hf(hf, device=device, max_batch=min(max_batch, 1024))
         return m, (3, 224, 224), f"{name} random-init (bf16)"
     if name in ("attention", "ffn"):
         from .. import torch_layers as tl

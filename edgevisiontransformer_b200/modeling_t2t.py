@@ -64,7 +64,7 @@ class _Performer:
 class B200T2TViT(nn.Module):
     """get_t2t_vit_{7,10,12,14} (t2t_vit.py:138-148) on libevt.  ``sd`` uses the oracle / INTEGRATION.md naming."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], depth: int, num_heads: int, device="cuda", max_batch: int = 256,
+    def __init__(self, sd: Dict[str, torch.Tensor], depth: int, num_heads: int, device="cuda", max_batch: int = 1024,
                  precision: str = "bf16"):
         super().__init__()
         dev = torch.device(device)

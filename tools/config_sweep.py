@@ -60,8 +60,8 @@ def main():
         ("small_bs256", "deit_small", 256, 256, "bf16"),
         ("base_bs4096", "deit_base", 4096, 1024, "bf16"),
         ("pruned_tiny_bs1024", "pruned", 1024, 1024, "bf16"),
-        ("t2t14_bs1024", "t2t_vit_14", 1024, 256, "bf16"),
-        ("swin_tiny_bs1024", "swin_tiny", 1024, 256, "bf16"),      # SURVEY.md section 8f rank 4 (not a BASELINE config)
+        ("t2t14_bs1024", "t2t_vit_14", 1024, 1024, "bf16"),
+        ("swin_tiny_bs1024", "swin_tiny", 1024, 1024, "bf16"),      # SURVEY.md section 8f rank 4 (not a BASELINE config)
     ]
     for name, kind, batch, chunk, prec in cases:
         if only and not any(o in name for o in only):
