@@ -199,6 +199,95 @@ __global__ void __launch_bounds__(256) unfold_ln_rows_kernel(const TIN* __restri
   }
 }
 
+// The 7 x 7 x 3 soft split of T2T's first stage (147 elements per output row = 7 runs of 21 contiguous floats), rewritten for
+// instruction count: the generic kernel above issued ~660 warp instructions per output row here (ncu: issue slots 85 % busy --
+// per-element validity branches, 64-bit address arithmetic and gamma / beta reloaded per row) and ran at 283 us per 256 images
+// against a 61 us HBM floor.  Lane l owns elements l, l + 32, ... (consecutive lanes read consecutive floats of a run), their
+// offsets, window coordinates and affine parameters are row-invariant registers, interior windows (93 % of a 56 x 56 grid) take
+// a path without any bounds test.  Several output rows per warp, one after the other.
+template <typename TIN, bool LN, int ROWS>
+__global__ void __launch_bounds__(256) unfold773_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                        int H, int W, int s, int p, int oh, int ow, long long rows) {
+  constexpr int KK = 7, CC = 3, L = KK * KK * CC, kRun = KK * CC, NE = (L + 31) / 32;  // 147, 21, 5
+  const int lane = threadIdx.x & 31;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
+  int off[NE], ky[NE], kx[NE];
+  float g[NE], be[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int e = lane + 32 * i;
+    const bool in = e < L;
+    ky[i] = in ? e / kRun : 0;
+    const int r = in ? e - ky[i] * kRun : 0;
+    kx[i] = r / CC;
+    off[i] = in ? ky[i] * W * CC + r : -1;
+    g[i] = (LN && in) ? gamma[e] : 0.f;
+    be[i] = (LN && in) ? beta[e] : 0.f;
+  }
+  const int npad = static_cast<int>(ldo);  // elements L .. ldo-1 of a row are zero padding
+  int ox = static_cast<int>(row0 % ow);
+  long long t = row0 / ow;
+  int oy = static_cast<int>(t % oh);
+  long long b = t / oh;
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) break;
+    const int iy0 = oy * s - p, ix0 = ox * s - p;
+    const TIN* base = x + ((b * H + iy0) * static_cast<long long>(W) + ix0) * CC;
+    float v[NE];
+    if (iy0 >= 0 && iy0 + KK <= H && ix0 >= 0 && ix0 + KK <= W) {
+#pragma unroll
+      for (int i = 0; i < NE - 1; ++i) v[i] = static_cast<float>(base[off[i]]);
+      v[NE - 1] = off[NE - 1] >= 0 ? static_cast<float>(base[off[NE - 1]]) : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int iy = iy0 + ky[i], ix = ix0 + kx[i];
+        const bool ok = off[i] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        v[i] = ok ? static_cast<float>(base[off[i]]) : 0.f;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (LN) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) sum += v[i];
+      mean = warp_sum(sum) / static_cast<float>(L);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NE - 1; ++i) {
+        const float d = v[i] - mean;
+        q += d * d;
+      }
+      if (off[NE - 1] >= 0) {
+        const float d = v[NE - 1] - mean;
+        q += d * d;
+      }
+      rstd = rsqrtf(warp_sum(q) / static_cast<float>(L) + eps);
+    }
+    __nv_bfloat16* orow = out + row * ldo;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int e = lane + 32 * i;
+      if (i < NE - 1 || e < npad) {
+        float o = LN ? (v[i] - mean) * rstd * g[i] + be[i] : v[i];
+        if (i == NE - 1 && off[i] < 0) o = 0.f;
+        orow[e] = __float2bfloat16_rn(o);
+      }
+    }
+    if (++ox == ow) {
+      ox = 0;
+      if (++oy == oh) {
+        oy = 0;
+        ++b;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- performer
 // Both kernels are chains of small matrix products per 16-token tile and run them on the warp-level tensor path
 // (mma.sync m16n8k16, bf16 operands, f32 accumulate) -- the first version walked them with 128 warp shuffles per token
@@ -677,7 +766,8 @@ void unfold_ln_dispatch(const TIN* xi, __nv_bfloat16* o, int64_t ldo, const floa
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   constexpr int kRowsPerWarp = 4;
   const unsigned grid_rows = static_cast<unsigned>((rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp));
-  if (k == 7 && C == 3) unfold_ln_rows_kernel<TIN, LN, 7, 3, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
+  if (k == 7 && C == 3 && ldo <= 160) unfold773_kernel<TIN, LN, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
+  else if (k == 7 && C == 3) unfold_ln_rows_kernel<TIN, LN, 7, 3, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
   else if (k == 3 && C == 64) unfold_ln_kernel<TIN, LN, 3, 64><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
   else unfold_ln_kernel<TIN, LN, 0, 0><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
 }
