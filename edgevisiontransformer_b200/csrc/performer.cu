@@ -199,53 +199,57 @@ __global__ void __launch_bounds__(256) unfold_ln_rows_kernel(const TIN* __restri
   }
 }
 
-// The 7 x 7 x 3 soft split of T2T's first stage (147 elements per output row = 7 runs of 21 contiguous floats), rewritten for
+// The 7 x 7 x 3 soft split of T2T's first stage (147 elements per output row = 7 runs of 21 contiguous floats), written for
 // instruction count: the generic kernel above issued ~660 warp instructions per output row here (ncu: issue slots 85 % busy --
-// per-element validity branches, 64-bit address arithmetic and gamma / beta reloaded per row) and ran at 283 us per 256 images
-// against a 61 us HBM floor.  Lane l owns elements l, l + 32, ... (consecutive lanes read consecutive floats of a run), their
-// offsets, window coordinates and affine parameters are row-invariant registers, interior windows (93 % of a 56 x 56 grid) take
-// a path without any bounds test.  Several output rows per warp, one after the other.
-template <typename TIN, bool LN, int ROWS>
+// per-element validity branches, 64-bit address arithmetic, gamma / beta reloaded per row) and ran at 283 us per 256 images
+// against a 61 us HBM floor; one row per warp with row-invariant registers still took ~220 (205 us, issue slots 76 %).
+// Here EIGHT lanes share an output row (four rows per warp at a time): lane j of the group owns elements j, j + 8, ..., j + 144
+// (19 each, 8 x 19 = 152 = the padded row length), so a row costs three shuffle levels per reduction instead of five, the
+// per-row bookkeeping is shared by four rows, and 19 independent loads per lane are in flight.  Offsets and affine parameters
+// of the lane's elements are row-invariant registers; a group of four windows that are all interior (83 % of a 56 x 56 grid)
+// takes a path without any bounds test.
+template <typename TIN, bool LN, int ITER>
 __global__ void __launch_bounds__(256) unfold773_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out, long long ldo,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                         int H, int W, int s, int p, int oh, int ow, long long rows) {
-  constexpr int KK = 7, CC = 3, L = KK * KK * CC, kRun = KK * CC, NE = (L + 31) / 32;  // 147, 21, 5
+  constexpr int KK = 7, CC = 3, L = KK * KK * CC, kRun = KK * CC, NE = 19;  // 147, 21; 8 lanes x 19 elements = 152
   const int lane = threadIdx.x & 31;
-  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
-  if (row0 >= rows) return;
-  int off[NE], ky[NE], kx[NE];
+  const int j = lane & 7, slot = lane >> 3;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int off[NE];
   float g[NE], be[NE];
 #pragma unroll
   for (int i = 0; i < NE; ++i) {
-    const int e = lane + 32 * i;
+    const int e = j + 8 * i;
     const bool in = e < L;
-    ky[i] = in ? e / kRun : 0;
-    const int r = in ? e - ky[i] * kRun : 0;
-    kx[i] = r / CC;
-    off[i] = in ? ky[i] * W * CC + r : -1;
+    const int ky = in ? e / kRun : 0;
+    off[i] = in ? ky * W * CC + (e - ky * kRun) : -1;
     g[i] = (LN && in) ? gamma[e] : 0.f;
     be[i] = (LN && in) ? beta[e] : 0.f;
   }
-  const int npad = static_cast<int>(ldo);  // elements L .. ldo-1 of a row are zero padding
-  int ox = static_cast<int>(row0 % ow);
-  long long t = row0 / ow;
-  int oy = static_cast<int>(t % oh);
-  long long b = t / oh;
 #pragma unroll 1
-  for (int rr = 0; rr < ROWS; ++rr) {
-    const long long row = row0 + rr;
-    if (row >= rows) break;
+  for (int it = 0; it < ITER; ++it) {
+    const long long row = (warp_id * ITER + it) * 4 + slot;
+    const bool live = row < rows;
+    const long long rc = live ? row : rows - 1;  // dead slots recompute the last row and store nothing (shuffles stay uniform)
+    const int ox = static_cast<int>(rc % ow);
+    const long long t = rc / ow;
+    const int oy = static_cast<int>(t % oh);
+    const long long b = t / oh;
     const int iy0 = oy * s - p, ix0 = ox * s - p;
     const TIN* base = x + ((b * H + iy0) * static_cast<long long>(W) + ix0) * CC;
+    const bool interior = iy0 >= 0 && iy0 + KK <= H && ix0 >= 0 && ix0 + KK <= W;
     float v[NE];
-    if (iy0 >= 0 && iy0 + KK <= H && ix0 >= 0 && ix0 + KK <= W) {
+    if (__all_sync(0xffffffffu, interior)) {
 #pragma unroll
       for (int i = 0; i < NE - 1; ++i) v[i] = static_cast<float>(base[off[i]]);
       v[NE - 1] = off[NE - 1] >= 0 ? static_cast<float>(base[off[NE - 1]]) : 0.f;
     } else {
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const int iy = iy0 + ky[i], ix = ix0 + kx[i];
+        const int e = j + 8 * i;
+        const int ky = e / kRun, kx = (e - ky * kRun) / CC;
+        const int iy = iy0 + ky, ix = ix0 + kx;
         const bool ok = off[i] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W;
         v[i] = ok ? static_cast<float>(base[off[i]]) : 0.f;
       }
@@ -255,7 +259,10 @@ __global__ void __launch_bounds__(256) unfold773_kernel(const TIN* __restrict__ 
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) sum += v[i];
-      mean = warp_sum(sum) / static_cast<float>(L);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      mean = sum / static_cast<float>(L);
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < NE - 1; ++i) {
@@ -266,23 +273,18 @@ __global__ void __launch_bounds__(256) unfold773_kernel(const TIN* __restrict__ 
         const float d = v[NE - 1] - mean;
         q += d * d;
       }
-      rstd = rsqrtf(warp_sum(q) / static_cast<float>(L) + eps);
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      rstd = rsqrtf(q / static_cast<float>(L) + eps);
     }
-    __nv_bfloat16* orow = out + row * ldo;
+    if (live) {
+      __nv_bfloat16* orow = out + row * ldo + j;
 #pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      const int e = lane + 32 * i;
-      if (i < NE - 1 || e < npad) {
+      for (int i = 0; i < NE; ++i) {
         float o = LN ? (v[i] - mean) * rstd * g[i] + be[i] : v[i];
-        if (i == NE - 1 && off[i] < 0) o = 0.f;
-        orow[e] = __float2bfloat16_rn(o);
-      }
-    }
-    if (++ox == ow) {
-      ox = 0;
-      if (++oy == oh) {
-        oy = 0;
-        ++b;
+        if (i == NE - 1 && off[i] < 0) o = 0.f;  // elements 147 .. 151: the zero padding of the row
+        orow[8 * i] = __float2bfloat16_rn(o);
       }
     }
   }
@@ -766,7 +768,11 @@ void unfold_ln_dispatch(const TIN* xi, __nv_bfloat16* o, int64_t ldo, const floa
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   constexpr int kRowsPerWarp = 4;
   const unsigned grid_rows = static_cast<unsigned>((rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp));
-  if (k == 7 && C == 3 && ldo <= 160) unfold773_kernel<TIN, LN, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
+  if (k == 7 && C == 3 && ldo == 152) {
+    constexpr int kIter = 2;  // 8 warps x 4 rows x 2 iterations = 64 rows per block
+    const unsigned g773 = static_cast<unsigned>((rows + 64 - 1) / 64);
+    unfold773_kernel<TIN, LN, kIter><<<g773, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
+  }
   else if (k == 7 && C == 3) unfold_ln_rows_kernel<TIN, LN, 7, 3, kRowsPerWarp><<<grid_rows, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, H, W, s, p, oh, ow, rows);
   else if (k == 3 && C == 64) unfold_ln_kernel<TIN, LN, 3, 64><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
   else unfold_ln_kernel<TIN, LN, 0, 0><<<grid, 256, 0, st>>>(xi, o, ldo, gamma, beta, eps, B, H, W, C, k, s, p, oh, ow, rows);
