@@ -93,6 +93,7 @@ class PipelinedClassifier:
         self._pinned_out = {}
         self._pinned_sel = {}
         self._last = None              # handle of the most recent submit (steady state = it is still running)
+        self._next_buf = 0
 
     @torch.no_grad()
     def _run(self, host_pixels: torch.Tensor, want_logits: bool, ramp: bool = True):
@@ -131,8 +132,11 @@ class PipelinedClassifier:
             host_out = pair[sel]
         # (no re-recording of the `free` events here: each was last recorded after the forward that read its buffer, possibly
         #  in the previous call -- waiting for exactly that forward is what lets this call's first copies start early)
-        for i, (s, e) in enumerate(bounds):
-            k = i & 1
+        for s, e in bounds:
+            # the two staging buffers alternate ACROSS calls too: with one chunk per call (batch <= chunk) a per-call index would
+            # put every batch in buffer 0 and the next batch's copy would wait for this batch's forward
+            k = self._next_buf
+            self._next_buf ^= 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._free[k])          # buffer k no longer read by forward i-2
                 bufs[k][: e - s].copy_(host_pixels[s:e], non_blocking=True)
