@@ -39,6 +39,16 @@ constexpr int kResBytes = BM * 128;        // ring entry: 128 rows x 32 f32
 constexpr int kXnStgBytes = 32 * 64;       // bf16 staging tile of one epilogue warp: 32 rows x 32 bf16, 64B-swizzled
 constexpr int kMaxD = 384;
 constexpr int kSmemLimit = 232448;
+// A/B knobs of the D = 384 configuration (build.py: EVT_NVCC_EXTRA): operand stages of the K loop against residual-ring depth
+#ifndef EVT_ROWLN_STAGES2
+#define EVT_ROWLN_STAGES2 3
+#endif
+#ifndef EVT_ROWLN_DEPTH2
+#define EVT_ROWLN_DEPTH2 6
+#endif
+#ifndef EVT_ROWLN_DEPTHMIN_COPY2
+#define EVT_ROWLN_DEPTHMIN_COPY2 4
+#endif
 
 struct RowLnParams {
   const float* bias;   // [D] or null
@@ -64,7 +74,7 @@ struct CfgR {
   // NT == 1: two accumulator slots double-buffer the row blocks, the K loop is short and hidden -> two stages are enough.
   // NT == 2: one K loop per slot (the A tile is re-read from L2), so that pass 1 of slot 0 runs under the MMAs of slot 1.  A
   // single K loop feeding both slots (A read once, 40 KB stages) measured slower: out-proj 66 vs 56 us at D = 384.
-  static constexpr int kStages = NT == 1 ? 2 : 3;
+  static constexpr int kStages = NT == 1 ? 2 : EVT_ROWLN_STAGES2;
   static constexpr int kCopyBytes = COPY ? EW * kStgBytes : 0;  // f32 staging of the normalised rows (TF dialect)
   static constexpr int kVecBytes = 3 * kMaxD * 4;               // bias, gamma, beta
   static constexpr int kStatBytes = 2 * G * BM * 4;             // [sum | squares][column group][row]
@@ -73,8 +83,8 @@ struct CfgR {
   // multiple of G -- then an entry is only ever consumed by ONE group, and a consumer has seen round k-1 of an entry before
   // it waits for round k.  (A depth of 5 with two groups deadlocked: a group waiting for round 1 of an entry whose round 0 --
   // the other group's chunk -- had not landed yet passed its parity wait on the untouched barrier.)
-  static constexpr int kDepthWant = G == 4 ? 8 : 6;
-  static constexpr int kDepthMin = G == 3 ? 3 : 4;
+  static constexpr int kDepthWant = G == 4 ? 8 : (NT == 2 ? EVT_ROWLN_DEPTH2 : 6);
+  static constexpr int kDepthMin = G == 3 ? 3 : (NT == 2 && COPY ? EVT_ROWLN_DEPTHMIN_COPY2 : 4);
   static constexpr int kResDepth = (kFixed + EW * kXnStgBytes + kDepthWant * kResBytes <= kSmemLimit) ? kDepthWant : kDepthMin;
   // (the TF-dialect variant stores the f32 rows from a single staging tile in the same bulk group: one tile there too)
   static constexpr int kXnBufs = (!COPY && kFixed + kResDepth * kResBytes + 2 * EW * kXnStgBytes <= kSmemLimit) ? 2 : 1;
@@ -475,7 +485,10 @@ bool gemm_rowln_supported(int64_t M, int N, int K, bool copy_ln) {
 // shape allows).  D = 384 holds a row block in BOTH accumulator slots, so the MMAs of the next block cannot run under the
 // epilogue: with a long K loop (HF DeiT-Small FC2, K = 1536: 104 us against 72 + 25 for the two kernels) the fusion loses; it
 // wins for the out-projection (56 against 41 + 25) and in the TF dialect, whose LayerNorm kernel also writes the f32 rows back.
-bool gemm_rowln_pays(int N, int K, bool copy_ln) { return N == kSlotCols || copy_ln || K <= 2 * kSlotCols; }
+bool gemm_rowln_pays(int N, int K, bool copy_ln) {
+  static const bool always = getenv("EVT_ROWLN_ALWAYS") != nullptr && atoi(getenv("EVT_ROWLN_ALWAYS")) != 0;  // A/B timing
+  return always || N == kSlotCols || copy_ln || K <= 2 * kSlotCols;
+}
 
 int gemm_rowln_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* resid, int64_t ldr,
                       const float* gamma, const float* beta, float eps, bool copy_ln, void* xn, int64_t ldxn, int64_t M, int N,
