@@ -252,3 +252,24 @@ def test_two_independent_t2t_front_end_restatements_agree():
     assert np.array_equal(u, t2t_np.soft_split(x.double().numpy(), 7, 4, 2))
     y = torch.randn(1, 28, 28, 8, generator=torch.Generator().manual_seed(1))
     assert np.array_equal(ot2t.unfold_nhwc(y, 3, 2, 1).double().numpy(), t2t_np.soft_split(y.double().numpy(), 3, 2, 1))
+
+
+def test_two_tf_dialect_restatements_agree_and_einops_patterns_hold():
+    """oracle/tf_vit.py (torch, hand-written permutes) against oracle/tf_vit_np.py (NumPy float64; every re-layout through
+    einops.rearrange with the reference's own pattern strings, modeling/models/vit.py:33-34, modeling/layers/attention.py:19-20):
+    the patch pixel order (p1 p2 c), the fused (qkv h d) column order and the head merge are pinned to the library the reference
+    calls; the LN-in-skip dataflow would have to be misread twice.  Uneven heads / FFN widths = ViT_Pruned 'layerwise'."""
+    from oracle import tf_vit_np
+    for kw, seed in ((dict(dim=192, depth=2), 0), (dict(dim=128, depth=3, heads=[1, 2, 1], inter=[230, 64, 407], mlp_dim=96), 3)):
+        sd, heads, _ = otf.init_tf_vit(seed=seed, stress=True, **kw)
+        x = ovit.synthetic_images(2, seed=seed + 1)
+        a = otf.tf_vit_forward(sd, x, heads).double().numpy()
+        b = tf_vit_np.tf_vit_forward_np(sd, x, heads)
+        assert a.shape == b.shape == (2, 1000)
+        assert np.abs(a - b).max() < 2e-4 * max(1.0, np.abs(b).max()), np.abs(a - b).max()
+        assert (a.argmax(-1) == b.argmax(-1)).all()
+    # the hand-written patch flattening of oracle/tf_vit.py is bit-identical to the einops pattern (a pure gather)
+    from einops import rearrange
+    img = torch.randn(2, 3, 32, 48)
+    mine = img.reshape(2, 3, 2, 16, 3, 16).permute(0, 2, 4, 3, 5, 1).reshape(2, 6, 768)
+    assert torch.equal(mine, rearrange(img, tf_vit_np.PATCHES, p1=16, p2=16))
