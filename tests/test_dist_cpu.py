@@ -68,3 +68,19 @@ def test_chunk_schedule_properties():
             assert all(s[i] <= 3 * s[i - 1] for i in range(1, len(s))), (batch, chunk, s)
     assert chunk_schedule(4096, 1024) == [128, 384, 512, 1024, 1024, 1024]
     assert chunk_schedule(512, 512) == [64, 192, 256]
+
+
+def test_uniform_schedule_properties():
+    """Steady-state schedule of `PipelinedClassifier.submit` (the previous batch still runs, nothing to ramp for): full chunks,
+    never more than the chunk, and no tail shorter than half a chunk -- a short tail is split evenly with its neighbour."""
+    from edgevisiontransformer_b200.eval_loop import uniform_schedule
+    for batch in (1, 6, 63, 64, 100, 511, 512, 513, 1000, 1024, 1030, 2048, 2100, 4095, 4096, 5000):
+        for chunk in (4, 64, 256, 512, 1024):
+            s = uniform_schedule(batch, chunk)
+            assert sum(s) == batch and all(0 < n <= chunk for n in s), (batch, chunk, s)
+            if len(s) > 1:
+                assert min(s) >= chunk // 4, (batch, chunk, s)      # the evenly split tail is at least a quarter chunk
+    assert uniform_schedule(4096, 1024) == [1024] * 4
+    assert uniform_schedule(2100, 1024) == [1024, 538, 538]
+    assert uniform_schedule(1030, 1024) == [515, 515]
+    assert uniform_schedule(7, 1024) == [7]
