@@ -268,6 +268,39 @@ extern "C" int evt_im2col_patch(const float* pixels, void* cols, int B, int H, i
   if (rc != EVT_OK) return rc;
   return evt::im2col_launch(pixels, EVT_PIX_F32, nullptr, nullptr, cols, EVT_BF16, B, H, W, P, static_cast<cudaStream_t>(stream));
 }
+// ViTEmbeddings.forward as ONE op-level call (SURVEY.md section 8 rows a1 + a2): the same three launches the model runtime
+// issues -- patch gather with one row per TOKEN (prefix rows zero), residual rows preset to pos + (prefix token | conv bias),
+// tcgen05 GEMM whose TMA reduce-add epilogue adds the projections.
+extern "C" int evt_patch_embed_workspace_bytes(int B, int H, int W, int P, int n_prefix, size_t* out) {
+  EVT_CHECK_ARG(out != nullptr, "patch_embed: null out");
+  EVT_CHECK_ARG(B > 0 && H > 0 && W > 0 && P > 0 && n_prefix > 0 && H % P == 0 && W % P == 0, "patch_embed: bad sizes");
+  const size_t tokens = static_cast<size_t>(n_prefix) + static_cast<size_t>(H / P) * (W / P);
+  *out = static_cast<size_t>(B) * tokens * 3 * P * P * 2;
+  return EVT_OK;
+}
+extern "C" int evt_patch_embed_fwd(const void* pixels, int pixel_dtype, const float* pixel_scale, const float* pixel_bias,
+                                   const void* W, int64_t ldw, const float* bias, const float* prefix, const float* pos,
+                                   float* out, void* workspace, int B, int H, int Wd, int P, int D, int n_prefix,
+                                   evt_stream stream) {
+  int rc = evt_device_check();
+  if (rc != EVT_OK) return rc;
+  EVT_CHECK_ARG(pixels && W && bias && prefix && pos && out && workspace, "patch_embed: null pointer");
+  EVT_CHECK_ARG(B > 0 && H > 0 && Wd > 0 && P > 0 && D > 0 && n_prefix > 0, "patch_embed: sizes must be positive");
+  EVT_CHECK_ARG(H % P == 0 && Wd % P == 0, "patch_embed: image size must be a multiple of the patch size");
+  const int K = 3 * P * P;
+  EVT_CHECK_ARG(D % 4 == 0 && ldw >= K && ldw % 8 == 0, "patch_embed: D must be a multiple of 4, ldw a multiple of 8 and >= 3*P*P");
+  EVT_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "patch_embed: workspace must be 1 KiB aligned");
+  const int tokens = n_prefix + (H / P) * (Wd / P);
+  const long long M = static_cast<long long>(B) * tokens;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t row_bytes = static_cast<size_t>(K) * 2;
+  EVT_CUDA(cudaMemset2DAsync(workspace, tokens * row_bytes, 0, n_prefix * row_bytes, B, st));
+  rc = evt::im2col_launch(pixels, pixel_dtype, pixel_scale, pixel_bias, workspace, EVT_BF16, B, H, Wd, P, st, tokens, n_prefix);
+  if (rc != EVT_OK) return rc;
+  rc = evt::embed_fill_launch(prefix, pos, bias, out, B, tokens, n_prefix, D, st);
+  if (rc != EVT_OK) return rc;
+  return evt::gemm_launch(workspace, K, W, ldw, EVT_BF16, nullptr, out, D, 0, 0, out, EVT_F32, D, 0, 0, 0, M, D, K, EVT_ACT_NONE, st);
+}
 extern "C" int evt_prefix_tokens(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix,
                                  int D, evt_stream stream) {
   int rc = evt_device_check();

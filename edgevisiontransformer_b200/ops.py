@@ -250,6 +250,50 @@ def im2col_patch(pixels: torch.Tensor, patch: int = 16) -> torch.Tensor:
     return cols
 
 
+def patch_embed(pixels: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, prefix: torch.Tensor, pos: torch.Tensor,
+                patch: int = 16, mean=None, std=None) -> torch.Tensor:
+    """`ViTEmbeddings.forward` (SITE/models/vit/modeling_vit.py:95-126) as one library call: NCHW pixels (f32, bf16, or raw
+    uint8 with per-channel `mean` / `std` of the reference's `Normalize`, deit_pruning/src/utils.py:105-107) ->
+    f32 [B, tokens, D].  weight: the conv kernel [D, 3, P, P] (or [D, 3*P*P]); prefix: [n_prefix, D] cls (+ distillation)
+    token rows; pos: [tokens, D]."""
+    import ctypes as C
+    _need_cuda(pixels, weight, bias, prefix, pos)
+    if pixels.dim() != 4 or pixels.shape[1] != 3:
+        raise ValueError("patch_embed wants NCHW pixels with 3 channels")
+    pix = {torch.float32: _lib.PIX_F32, torch.bfloat16: _lib.PIX_BF16, torch.uint8: _lib.PIX_U8}.get(pixels.dtype)
+    if pix is None:
+        raise ValueError("patch_embed: pixels must be f32, bf16 or uint8")
+    pixels = pixels.contiguous()
+    B, _, H, W = pixels.shape
+    D = weight.shape[0]
+    K = 3 * patch * patch
+    w = weight.reshape(D, -1)
+    if w.shape[1] != K:
+        raise ValueError(f"patch_embed: weight has {w.shape[1]} inputs per filter, expected {K}")
+    w = w.to(torch.bfloat16).contiguous()
+    prefix = prefix.reshape(-1, D).float().contiguous()
+    tokens = prefix.shape[0] + (H // patch) * (W // patch)
+    pos = pos.reshape(-1, D).float().contiguous()
+    if pos.shape[0] != tokens:
+        raise ValueError(f"patch_embed: {pos.shape[0]} position rows for {tokens} tokens")
+    scale = shift = None
+    if pix == _lib.PIX_U8:
+        if mean is None or std is None:
+            raise ValueError("patch_embed: uint8 pixels need mean and std")
+        scale = (C.c_float * 3)(*[1.0 / (255.0 * float(s_)) for s_ in std])
+        shift = (C.c_float * 3)(*[-float(m_) / float(s_) for m_, s_ in zip(mean, std)])
+    lib = _lib.load()
+    n = C.c_size_t()
+    _lib.check(lib.evt_patch_embed_workspace_bytes(B, H, W, patch, prefix.shape[0], C.byref(n)), "patch_embed_workspace_bytes")
+    ws = torch.empty(n.value + 1024, dtype=torch.uint8, device=pixels.device)
+    ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    out = torch.empty((B, tokens, D), dtype=torch.float32, device=pixels.device)
+    _lib.check(lib.evt_patch_embed_fwd(pixels.data_ptr(), pix, scale, shift, w.data_ptr(), K, bias.float().contiguous().data_ptr(),
+                                       prefix.data_ptr(), pos.data_ptr(), out.data_ptr(), ws_ptr, B, H, W, patch, D,
+                                       prefix.shape[0], _stream()), "patch_embed")
+    return out
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     x = x.contiguous()

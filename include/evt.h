@@ -166,6 +166,22 @@ int evt_attention_fwd_tf32(const float* qkv, int64_t ldq, float* ctx, int64_t ld
  * (ViT / DeiT: 16; Swin: 4). */
 int evt_im2col_patch(const float* pixels, void* cols, int B, int H, int W, int P, evt_stream stream);
 
+/* ViTEmbeddings.forward as one op-level call (SITE/models/vit/modeling_vit.py:95-126 = cls / distillation token,
+ * position embeddings; :151-167 = ViTPatchEmbeddings, Conv2d(3, D, P, P) as an im2col GEMM):
+ *   out[b, t, :] = pos[t, :] + (t < n_prefix ? prefix[t, :] : bias + W . patch(b, t - n_prefix))
+ * pixels    NCHW [B,3,H,W] of pixel_dtype (evt_pixel_dtype: f32, bf16 or raw u8; u8 takes pixel_scale / pixel_bias,
+ *           3 HOST floats each, applied as x * scale[c] + bias[c] inside the patch gather; NULL otherwise)
+ * W         bf16 [D, ldw], K order (c, i, j) = conv.weight.reshape(D, -1); ldw >= 3*P*P, multiple of 8
+ * bias      f32 [D]; prefix f32 [n_prefix, D] (cls, or cls + distillation token); pos f32 [tokens, D]
+ * out       f32 [B * tokens, D], tokens = n_prefix + (H/P)*(W/P)
+ * workspace evt_patch_embed_workspace_bytes bytes, 1 KiB aligned (the bf16 patch matrix, one row per token)
+ * P a multiple of 8.  Three launches (patch gather, row preset, tcgen05 GEMM with a TMA reduce-add epilogue). */
+int evt_patch_embed_workspace_bytes(int B, int H, int W, int P, int n_prefix, size_t* out);
+int evt_patch_embed_fwd(const void* pixels, int pixel_dtype, const float* pixel_scale, const float* pixel_bias,
+                        const void* W, int64_t ldw, const float* bias, const float* prefix, const float* pos,
+                        float* out, void* workspace, int B, int H, int Wd, int P, int D, int n_prefix,
+                        evt_stream stream);
+
 /* Rows [0, n_prefix) of each image's token block: out[b, t, :] = prefix[t, :] + pos[t, :]
  * (cls / distillation token + position embedding, SITE/models/vit/modeling_vit.py:117-126). */
 int evt_prefix_tokens(const float* prefix, const float* pos, float* out, int B, int tokens, int n_prefix,

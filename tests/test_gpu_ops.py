@@ -421,6 +421,43 @@ def test_im2col_and_cast_and_unfold():
     assert torch.equal(u[:, :147].cpu(), refu.bfloat16()) and u[:, 147:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("kind,B,D", [("vit", 3, 192), ("deit", 2, 384), ("vit", 140, 192)])
+def test_patch_embed_matches_hf_embeddings(kind, B, D):
+    """evt_patch_embed_fwd = `ViTEmbeddings.forward` / `DeiTEmbeddings.forward` of the installed transformers (the module the
+    reference calls): Conv2d patch projection + cls (and distillation) token + position embeddings, f32 / bf16 / raw uint8
+    pixels.  The live HF module is the checker.  B = 140: 27 580 token rows, the CTA-pair GEMM path."""
+    from transformers import DeiTConfig, DeiTModel, ViTConfig, ViTModel
+    ops = _ops()
+    torch.manual_seed(11)
+    kw = dict(hidden_size=D, num_hidden_layers=1, num_attention_heads=D // 64, intermediate_size=2 * D)
+    emb = (ViTModel(ViTConfig(**kw), add_pooling_layer=False) if kind == "vit" else DeiTModel(DeiTConfig(**kw), add_pooling_layer=False)).embeddings.eval()
+    with torch.no_grad():
+        for prm in emb.parameters():
+            prm.copy_(torch.randn_like(prm) * (0.05 if prm.dim() == 4 else 0.5))
+    conv = emb.patch_embeddings.projection
+    prefix = emb.cls_token[0] if kind == "vit" else torch.cat((emb.cls_token[0], emb.distillation_token[0]), 0)
+    args = [t.detach().cuda() for t in (conv.weight, conv.bias, prefix, emb.position_embeddings[0])]
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        ref = emb(x)
+    out = ops.patch_embed(x.cuda(), *args)
+    assert out.shape == ref.shape == (B, 197 if kind == "vit" else 198, D)
+    # bf16 pixels and weights, f32 accumulation over K = 768: |sum| ~ 1.4, rounding ~ 2^-9 per operand
+    assert (out.cpu() - ref).abs().max().item() < 2e-2
+    assert torch.equal(out[:, : prefix.shape[0]].cpu(), (prefix + emb.position_embeddings[0, : prefix.shape[0]]).detach().expand(B, -1, -1))
+    outb = ops.patch_embed(x.bfloat16().cuda(), *args)
+    # the f32 path rounds its pixels to bf16 in the gather: same operands; split K at small M leaves the f32 add order open
+    assert (outb - out).abs().max().item() < 1e-4
+    if B <= 3:
+        mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)    # deit_pruning/src/utils.py:105-107
+        u8 = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8, generator=torch.Generator().manual_seed(13))
+        xn = (u8.float() / 255 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        with torch.no_grad():
+            refu = emb(xn)
+        outu = ops.patch_embed(u8.cuda(), *args, mean=mean, std=std)
+        assert (outu.cpu() - refu).abs().max().item() < 4e-2        # normalised pixels reach |x| ~ 2.6
+
+
 def test_errors_are_loud():
     ops = _ops()
     with pytest.raises(RuntimeError):
