@@ -29,6 +29,7 @@ class ModelSpec(C.Structure):
         ("act", C.c_int), ("eps", C.c_float),
         ("heads", C.c_int * MAX_LAYERS), ("inter", C.c_int * MAX_LAYERS),
         ("final_ln", C.c_int), ("head_hidden", C.c_int), ("t2t", C.c_int), ("precision", C.c_int), ("embed_k", C.c_int),
+        ("head_rows", C.c_int),
     ]
 
 

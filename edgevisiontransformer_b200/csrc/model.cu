@@ -148,7 +148,7 @@ Workspace plan_workspace(const evt_model* m, int batch, void* base) {
   const size_t o_ctx = take(M * amax * es);
   // the patch matrix has one row per TOKEN when the library builds it (pixels path), see forward_impl
   const size_t o_big = take(std::max(M * imax_ld, (s.embed_k > 0 ? Mp : M) * static_cast<size_t>(m->patch_k)) * es);
-  const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * es);
+  const size_t o_cls = take(static_cast<size_t>(batch) * s.hidden * (s.head_rows > 1 ? s.head_rows : 1) * es);
   const size_t o_hh = take(static_cast<size_t>(batch) * std::max(padn(s.head_hidden, m->pad), 8) * es);
   if (s.t2t) {
     for (int i = 0; i < 2; ++i) {
@@ -187,6 +187,10 @@ int validate_spec(const evt_model_spec* s) {
   EVT_CHECK_ARG(s->act == EVT_ACT_GELU_ERF || s->act == EVT_ACT_GELU_TANH, "FFN activation must be erf- or tanh-GELU");
   EVT_CHECK_ARG(s->eps > 0.f, "LayerNorm eps must be positive");
   EVT_CHECK_ARG(s->head_hidden >= 0, "head_hidden must be >= 0");
+  EVT_CHECK_ARG(s->head_rows >= 0 && s->head_rows <= 2, "head_rows must be 0 / 1 (cls row) or 2 (cls + distillation rows)");
+  if (s->head_rows == 2)
+    EVT_CHECK_ARG(s->tokens == patches + 2 && s->final_ln != 0 && s->head_hidden == 0,
+                  "head_rows = 2 (two-head distilled DeiT) needs 198 tokens, the final LayerNorm and a single Linear head");
   EVT_CHECK_ARG(s->precision == EVT_PREC_BF16 || s->precision == EVT_PREC_TF32, "precision must be bf16 (0) or tf32 (1)");
   EVT_CHECK_ARG(s->embed_k >= 0 && s->embed_k % 8 == 0, "embed_k must be a non-negative multiple of 8");
   if (s->t2t) {
@@ -412,7 +416,7 @@ extern "C" int evt_model_load_weights(evt_model* m, const evt_tensor_view* tenso
     EVT_TRY(L.vec("vit.layernorm.weight", D, false, &m->lnf_g));
     EVT_TRY(L.vec("vit.layernorm.bias", D, false, &m->lnf_b));
   }
-  int cls_in = D;
+  int cls_in = D * (s.head_rows > 1 ? s.head_rows : 1);
   if (s.head_hidden > 0) {
     EVT_TRY(L.mat("pre_classifier.weight", s.head_hidden, D, D, &m->w_pre));
     EVT_TRY(L.vec("pre_classifier.bias", s.head_hidden, true, &m->b_pre));
@@ -437,7 +441,7 @@ extern "C" int evt_model_launches_per_forward(const evt_model* m) {
   if (!m) return 0;
   const evt_model_spec& s = m->spec;
   // T2T front-end: per performer unfold+LN, kqv, 3 performer kernels (the last one carries attn_output + MLP); then the last soft split
-  return (s.t2t ? 2 * 5 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + 1 + (s.head_hidden > 0 ? 2 : 1);
+  return (s.t2t ? 2 * 5 + 1 : 0) + (s.embed_k > 0 ? 2 : 3) + 7 * s.layers + (s.final_ln && s.head_rows > 1 ? s.head_rows : 1) + (s.head_hidden > 0 ? 2 : 1);
 }
 
 static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts* opts, const void* patch_matrix, int64_t patch_ld,
@@ -624,8 +628,15 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
   }
   // head: only the cls row of every image is consumed (SITE/models/vit/modeling_vit.py:641)
   const int64_t tok_stride = static_cast<int64_t>(s.tokens) * D;
+  const int head_rows = s.head_rows > 1 ? s.head_rows : 1;
   if (s.final_ln) {
-    EVT_STAGE(EVT_STAGE_HEAD, layernorm_launch(w.resid, tok_stride, m->lnf_g, m->lnf_b, w.clsn, adt, D, nullptr, batch, D, s.eps, st));
+    // head_rows = 2 (DeiTForImageClassificationWithTeacher, SITE/models/deit/modeling_deit.py: logits = (cls_classifier(x[:, 0]) +
+    // distillation_classifier(x[:, 1])) / 2): rows 0 and 1 of every image are normalised side by side into one 2D-wide row, and
+    // ONE classifier GEMM with K = 2D over [W_cls | W_dist] / 2 produces the averaged logits.
+    for (int r = 0; r < head_rows; ++r)
+      EVT_STAGE(EVT_STAGE_HEAD, layernorm_launch(w.resid + static_cast<size_t>(r) * D, tok_stride, m->lnf_g, m->lnf_b,
+                                                 w.clsn + static_cast<size_t>(r) * D * m->es, adt, static_cast<int64_t>(head_rows) * D, nullptr,
+                                                 batch, D, s.eps, st));
   } else {
     const long long total = static_cast<long long>(batch) * D;
     const unsigned grid = static_cast<unsigned>((total + 255) / 256);
@@ -646,8 +657,9 @@ static int forward_impl(evt_model* m, const void* pixels, const evt_forward_opts
     EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.hh, hl, m->w_cls, hl, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
                         s.num_labels, s.head_hidden, EVT_ACT_NONE, st));
   } else {
-    EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.clsn, D, m->w_cls, D, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
-                        s.num_labels, D, EVT_ACT_NONE, st));
+    const int kc = head_rows * D;
+    EVT_STAGE(EVT_STAGE_HEAD, gemm_launch(w.clsn, kc, m->w_cls, kc, dt, m->b_cls, nullptr, 0, 0, 0, logits, EVT_F32, s.num_labels, 0, 0, 0, batch,
+                        s.num_labels, kc, EVT_ACT_NONE, st));
   }
 #undef EVT_STAGE
 #undef EVT_TRY

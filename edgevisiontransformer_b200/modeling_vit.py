@@ -41,6 +41,7 @@ class B200ViTConfig:
     precision: str = "bf16"           # "bf16" (2e-2 logit tolerance) | "tf32" (1e-3; f32 activations)
     embed_k: int = 0                  # >0: caller-built patch matrix with this K (T2T: 576), see forward_embedded
     t2t: bool = False                 # tokens-to-token front-end inside the library (NHWC f32 pixels; needs embed_k = 576)
+    head_rows: int = 1                # 2: DeiTForImageClassificationWithTeacher (cls + distillation rows feed ONE folded classifier)
 
     # names the reference's callers read off model.config
     @property
@@ -90,7 +91,9 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], *, layer_norm_eps=1e-12,
         final_ln = "vit.layernorm.weight" in sd
     if head_hidden is None:
         head_hidden = sd["pre_classifier.weight"].shape[0] if "pre_classifier.weight" in sd else 0
-    return B200ViTConfig(hidden_size=D, num_hidden_layers=L, heads=heads, intermediate=inter, head_size=head_size,
+    # normalise_keys folds the two heads of a distilled DeiT into one [num_labels, 2 D] classifier over the (cls | distillation) rows
+    head_rows = 2 if (not head_hidden and sd["classifier.weight"].shape[-1] == 2 * D) else 1
+    return B200ViTConfig(head_rows=head_rows, hidden_size=D, num_hidden_layers=L, heads=heads, intermediate=inter, head_size=head_size,
                          tokens=sd["vit.embeddings.position_embeddings"].shape[-2], image_size=image_size,
                          patch_size=patch_size, num_labels=sd["classifier.weight"].shape[0],
                          layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, dialect=dialect, final_ln=bool(final_ln),
@@ -146,6 +149,7 @@ class B200ViTForImageClassification(nn.Module):
         spec.head_hidden = int(config.head_hidden)
         spec.t2t = int(bool(config.t2t))
         spec.embed_k = int(config.embed_k)
+        spec.head_rows = int(config.head_rows)
         if config.precision not in ("bf16", "tf32"):
             raise ValueError(f"unsupported precision {config.precision!r}")
         spec.precision = _lib.PREC_TF32 if config.precision == "tf32" else _lib.PREC_BF16
@@ -474,13 +478,11 @@ def normalise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """Accept HF ViT ('vit.'), HF DeiT ('deit.') and DDP ('module.') prefixes.
 
     HF `DeiTForImageClassification` (198 tokens: cls + distillation token, ONE classifier on the cls row,
-    SITE/models/deit/modeling_deit.py:595-659) loads as it is.  `DeiTForImageClassificationWithTeacher` does not: its
-    logits are the mean of `cls_classifier(cls row)` and `distillation_classifier(distillation row)`, a second head this
-    runtime does not have -- such a checkpoint is refused rather than answered from the cls head alone."""
-    if any(k.split("module.")[-1].startswith(("distillation_classifier.", "cls_classifier.")) for k in sd):
-        raise ValueError("distilled DeiT checkpoint (DeiTForImageClassificationWithTeacher: cls_classifier + "
-                         "distillation_classifier, logits averaged over two heads) is not supported; load "
-                         "ViTForImageClassification / DeiTForImageClassification weights")
+    SITE/models/deit/modeling_deit.py:595-659) loads as it is.  `DeiTForImageClassificationWithTeacher` (the layout of the
+    public `facebook/deit-*-distilled-*` checkpoints) answers with the MEAN of `cls_classifier(cls row)` and
+    `distillation_classifier(distillation row)`: its two heads are folded here into one classifier over the concatenated
+    (cls | distillation) rows, `classifier.weight = [W_cls | W_dist] / 2`, `classifier.bias = (b_cls + b_dist) / 2`, which the
+    runtime evaluates as a single GEMM with K = 2 D (`evt_model_spec.head_rows = 2`).  Half of such a pair is refused."""
     out = {}
     for k, v in sd.items():
         if k.startswith("module."):
@@ -488,4 +490,16 @@ def normalise_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if k.startswith("deit."):
             k = "vit." + k[len("deit."):]
         out[k] = v
+    two = [k for k in out if k.startswith(("cls_classifier.", "distillation_classifier."))]
+    if two:
+        need = {"cls_classifier.weight", "cls_classifier.bias", "distillation_classifier.weight", "distillation_classifier.bias"}
+        if set(two) != need or "classifier.weight" in out:
+            raise ValueError("distilled DeiT checkpoint (DeiTForImageClassificationWithTeacher) needs cls_classifier and "
+                             f"distillation_classifier weight + bias and no third head; found {sorted(two)}")
+        wc, wd = out.pop("cls_classifier.weight"), out.pop("distillation_classifier.weight")
+        bc, bd = out.pop("cls_classifier.bias"), out.pop("distillation_classifier.bias")
+        if wc.shape != wd.shape:
+            raise ValueError("distilled DeiT checkpoint: the two heads differ in shape")
+        out["classifier.weight"] = torch.cat((wc.float(), wd.float()), dim=1) * 0.5
+        out["classifier.bias"] = (bc.float() + bd.float()) * 0.5
     return out

@@ -289,6 +289,11 @@ typedef struct evt_model_spec {
   int precision;               /* evt_precision: 0 bf16 operands, 1 tf32 operands (f32 activations) */
   int embed_k;                 /* 0: 3*patch*patch.  >0: K of the token-embedding GEMM when the caller builds the
                                   patch matrix itself (T2T: 3*3*64 = 576) and calls evt_model_forward_embedded */
+  int head_rows;               /* 0 / 1: the classifier reads the cls row.  2: HF DeiTForImageClassificationWithTeacher
+                                  (SITE/models/deit/modeling_deit.py, logits = (cls_classifier(x[:,0]) +
+                                  distillation_classifier(x[:,1])) / 2): rows 0 and 1 are normalised into one 2D-wide row
+                                  and "classifier.weight" is [num_labels, 2D] = [W_cls | W_dist] / 2, "classifier.bias"
+                                  = (b_cls + b_dist) / 2 (the Python loader builds both); needs tokens = patches + 2 */
 } evt_model_spec;
 
 typedef struct evt_tensor_view {

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layout_matches_header():
     from edgevisiontransformer_b200 import _lib
-    assert C.sizeof(_lib.ModelSpec) == 4 * 10 + 4 * 64 * 2 + 4 * 5
+    assert C.sizeof(_lib.ModelSpec) == 4 * 10 + 4 * 64 * 2 + 4 * 6        # ... embed_k, head_rows
     assert C.sizeof(_lib.TensorView) == 8 + 8 + 8 + 32
 
 

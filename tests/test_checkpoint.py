@@ -70,11 +70,22 @@ def test_key_normalisation():
     assert set(out) == {"vit.embeddings.cls_token", "classifier.weight"}
 
 
-def test_distilled_deit_checkpoint_is_refused():
-    """DeiTForImageClassificationWithTeacher averages two heads (cls + distillation row); answering from the cls head
-    alone would be silently wrong, so the loader refuses the layout (the timm path refuses head_dist the same way)."""
+def test_distilled_deit_heads_are_folded():
+    """DeiTForImageClassificationWithTeacher averages two heads (cls row, distillation row): normalise_keys folds them into
+    ONE classifier over the concatenated rows -- (W_c x_c + b_c + W_d x_d + b_d) / 2 == [W_c | W_d] / 2 . [x_c ; x_d] + (b_c + b_d) / 2 --
+    and refuses half a pair (answering from the cls head alone would be silently wrong)."""
     import pytest
+    g = torch.Generator().manual_seed(0)
+    wc, wd, bc, bd = (torch.randn(5, 8, generator=g), torch.randn(5, 8, generator=g), torch.randn(5, generator=g), torch.randn(5, generator=g))
+    sd = {"deit.embeddings.cls_token": torch.zeros(1, 1, 8), "cls_classifier.weight": wc, "cls_classifier.bias": bc,
+          "module.distillation_classifier.weight": wd, "distillation_classifier.bias": bd}
+    out = normalise_keys(sd)
+    assert set(out) == {"vit.embeddings.cls_token", "classifier.weight", "classifier.bias"}
+    xc, xd = torch.randn(3, 8, generator=g), torch.randn(3, 8, generator=g)
+    want = ((xc @ wc.T + bc) + (xd @ wd.T + bd)) / 2
+    got = torch.cat((xc, xd), 1) @ out["classifier.weight"].T + out["classifier.bias"]
+    assert torch.allclose(got, want, atol=1e-6)
     for extra in ("cls_classifier.weight", "distillation_classifier.weight", "module.distillation_classifier.bias"):
-        sd = {"deit.embeddings.cls_token": torch.zeros(1, 1, 8), extra: torch.zeros(2, 8)}
+        half = {"deit.embeddings.cls_token": torch.zeros(1, 1, 8), extra: torch.zeros(2, 8)}
         with pytest.raises(ValueError, match="distilled DeiT"):
-            normalise_keys(sd)
+            normalise_keys(half)

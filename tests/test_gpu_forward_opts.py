@@ -166,12 +166,41 @@ def test_hf_deit_for_image_classification_198_tokens():
         want = hf(pixel_values=x).logits
     _check(m(x.cuda()).logits, want)
     _check(m.forward_graphed(x[:1].cuda()).logits, want[:1])
-    # the distilled two-head variant is refused, not answered from one head
-    from transformers import DeiTForImageClassificationWithTeacher
-    t = DeiTForImageClassificationWithTeacher(DeiTConfig(hidden_size=192, num_hidden_layers=1, num_attention_heads=3,
-                                                         intermediate_size=768, num_labels=10))
-    with pytest.raises(ValueError, match="distilled DeiT"):
-        B200ViTForImageClassification.from_hf(t)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_hf_distilled_deit_with_teacher_two_heads(precision):
+    """HF `DeiTForImageClassificationWithTeacher` (the public distilled DeiT layout): logits = mean of the cls head on row 0 and
+    the distillation head on row 1.  Both rows go through the final LayerNorm and ONE folded classifier GEMM (K = 2 D,
+    evt_model_spec.head_rows = 2); the live HF module is the checker."""
+    from transformers import DeiTConfig, DeiTForImageClassificationWithTeacher
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    cfg = DeiTConfig(hidden_size=192, num_hidden_layers=12, num_attention_heads=3, intermediate_size=768, num_labels=1000,
+                     attn_implementation="eager")
+    torch.manual_seed(21)
+    hf = DeiTForImageClassificationWithTeacher(cfg).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if n.endswith("bias") or "layernorm" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+        hf.deit.embeddings.cls_token.normal_(0, 0.02)
+        hf.deit.embeddings.distillation_token.normal_(0, 0.02)
+        hf.deit.embeddings.position_embeddings.normal_(0, 0.02)
+    m = B200ViTForImageClassification.from_hf(hf, precision=precision)
+    assert m.config.tokens == 198 and m.config.head_rows == 2
+    x = ovit.synthetic_images(5, seed=9)
+    with torch.no_grad():
+        o = hf(pixel_values=x)
+        want = o.logits
+        assert torch.allclose(want, (o.cls_logits + o.distillation_logits) / 2, atol=1e-6)
+    got = m(x.cuda()).logits
+    if precision == "tf32":
+        assert (got.cpu() - want).abs().max().item() < 1e-3
+    else:
+        _check(got, want)
+        _check(m.forward_graphed(x[:1].cuda()).logits, want[:1])
+    # the cls head alone would have been a different answer: the test inputs tell the two apart
+    assert (o.cls_logits - want).abs().max().item() > 5e-2
 
 
 def test_tf_dialect_in_tf32_mode_keeps_the_skip_connection_in_full_precision():
