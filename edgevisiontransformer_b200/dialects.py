@@ -62,12 +62,15 @@ def tf_vit_to_canonical(sd: Dict[str, torch.Tensor], heads: List[int], head_size
 def timm_vit_to_canonical(sd: Dict[str, torch.Tensor], patch: int = 16) -> Tuple[Dict[str, torch.Tensor], dict]:
     """timm ``VisionTransformer`` / facebookresearch DeiT state dict -> (canonical state dict, from_state_dict kwargs).
 
-    Accepts the hub checkpoints' ``{'model': state_dict}`` wrapper.  Distilled variants (``dist_token`` / ``head_dist``)
-    are not what the reference loads (utils.py:52-62 asks for ``deit_{type}_patch16_{224,384}``) and are rejected."""
+    Accepts the hub checkpoints' ``{'model': state_dict}`` wrapper.  The reference asks the hub for
+    ``deit_{type}_patch16_{224,384}`` (utils.py:52-62); the hub's distilled variants (``DistilledVisionTransformer``:
+    ``dist_token``, ``head_dist``, eval output ``(head(x[:, 0]) + head_dist(x[:, 1])) / 2``) map onto the two-head layout that
+    ``modeling_vit.normalise_keys`` folds into one classifier.  Half of that layout is refused."""
     if "model" in sd and isinstance(sd["model"], dict):
         sd = sd["model"]
-    if "dist_token" in sd or "head_dist.weight" in sd:
-        raise ValueError("distilled DeiT checkpoints (dist_token / head_dist) are not supported")
+    distilled = "dist_token" in sd
+    if distilled != ("head_dist.weight" in sd):
+        raise ValueError("distilled DeiT checkpoint needs both dist_token and head_dist")
     D = sd["cls_token"].shape[-1]
     out: Dict[str, torch.Tensor] = {
         "vit.embeddings.cls_token": sd["cls_token"].reshape(1, 1, D),
@@ -75,8 +78,13 @@ def timm_vit_to_canonical(sd: Dict[str, torch.Tensor], patch: int = 16) -> Tuple
         "vit.embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
         "vit.embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
         "vit.layernorm.weight": sd["norm.weight"], "vit.layernorm.bias": sd["norm.bias"],
-        "classifier.weight": sd["head.weight"], "classifier.bias": sd["head.bias"],
     }
+    if distilled:
+        out["vit.embeddings.distillation_token"] = sd["dist_token"].reshape(1, 1, D)
+        out["cls_classifier.weight"], out["cls_classifier.bias"] = sd["head.weight"], sd["head.bias"]
+        out["distillation_classifier.weight"], out["distillation_classifier.bias"] = sd["head_dist.weight"], sd["head_dist.bias"]
+    else:
+        out["classifier.weight"], out["classifier.bias"] = sd["head.weight"], sd["head.bias"]
     l = 0
     while f"blocks.{l}.attn.qkv.weight" in sd:
         p, q = f"blocks.{l}.", f"vit.encoder.layer.{l}."

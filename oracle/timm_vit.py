@@ -36,8 +36,13 @@ def hf_to_timm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         "patch_embed.proj.weight": sd["vit.embeddings.patch_embeddings.projection.weight"],
         "patch_embed.proj.bias": sd["vit.embeddings.patch_embeddings.projection.bias"],
         "norm.weight": sd["vit.layernorm.weight"], "norm.bias": sd["vit.layernorm.bias"],
-        "head.weight": sd["classifier.weight"], "head.bias": sd["classifier.bias"],
     }
+    if "cls_classifier.weight" in sd:     # HF DeiTForImageClassificationWithTeacher -> facebookresearch DistilledVisionTransformer
+        out["dist_token"] = sd["vit.embeddings.distillation_token"]
+        out["head.weight"], out["head.bias"] = sd["cls_classifier.weight"], sd["cls_classifier.bias"]
+        out["head_dist.weight"], out["head_dist.bias"] = sd["distillation_classifier.weight"], sd["distillation_classifier.bias"]
+    else:
+        out["head.weight"], out["head.bias"] = sd["classifier.weight"], sd["classifier.bias"]
     l = 0
     while f"vit.encoder.layer.{l}.attention.attention.query.weight" in sd:
         p, q = f"vit.encoder.layer.{l}.", f"blocks.{l}."
@@ -56,7 +61,9 @@ def timm_vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_heads: in
     B = x.shape[0]
     D = sd["cls_token"].shape[-1]
     t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
-    t = torch.cat([sd["cls_token"].expand(B, -1, -1), t], dim=1) + sd["pos_embed"]
+    # DistilledVisionTransformer.forward_features (facebookresearch/deit models.py): cls, dist, patches
+    pre = [sd["cls_token"].expand(B, -1, -1)] + ([sd["dist_token"].expand(B, -1, -1)] if "dist_token" in sd else [])
+    t = torch.cat(pre + [t], dim=1) + sd["pos_embed"]
     hd = D // num_heads
     l = 0
     while f"blocks.{l}.attn.qkv.weight" in sd:
@@ -72,4 +79,23 @@ def timm_vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_heads: in
         t = t + F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
         l += 1
     t = F.layer_norm(t, (D,), sd["norm.weight"], sd["norm.bias"], TIMM_EPS)
+    if "dist_token" in sd:                # eval mode: the two heads' outputs averaged
+        return (F.linear(t[:, 0], sd["head.weight"], sd["head.bias"]) + F.linear(t[:, 1], sd["head_dist.weight"], sd["head_dist.bias"])) / 2
     return F.linear(t[:, 0], sd["head.weight"], sd["head.bias"])
+
+
+def build_hf_distilled(seed: int = 31, layers: int = 2):
+    """Seeded random-init HF ``DeiTForImageClassificationWithTeacher`` (DeiT-Tiny width, eps 1e-6 as in timm) with biases, LayerNorm
+    affine and the token / position embeddings randomised: the checker of the distilled two-head layout."""
+    from transformers import DeiTConfig, DeiTForImageClassificationWithTeacher
+    torch.manual_seed(seed)
+    hf = DeiTForImageClassificationWithTeacher(DeiTConfig(hidden_size=192, num_hidden_layers=layers, num_attention_heads=3,
+                                                         intermediate_size=768, num_labels=1000, layer_norm_eps=1e-6,
+                                                         attn_implementation="eager")).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if n.endswith("bias") or "layernorm" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+        for t in (hf.deit.embeddings.cls_token, hf.deit.embeddings.distillation_token, hf.deit.embeddings.position_embeddings):
+            t.normal_(0, 0.02)
+    return hf

@@ -231,6 +231,22 @@ def test_timm_dialect(golden_dir):
     _check(B200ViTForImageClassification.from_timm(tsd, precision="tf32")(x.cuda()).logits, want, tol=1e-3)
 
 
+def test_timm_distilled_dialect():
+    """facebookresearch/deit hub ``deit_*_distilled_patch16_224`` layout (dist_token + head_dist, logits = mean of the two heads)
+    through from_timm; the checker is HF ``DeiTForImageClassificationWithTeacher`` (eps 1e-6) on the same weights."""
+    from edgevisiontransformer_b200 import B200ViTForImageClassification
+    from oracle import timm_vit as otimm
+    hf = otimm.build_hf_distilled(layers=12)
+    sd = {("vit." + k[5:] if k.startswith("deit.") else k): v.detach() for k, v in hf.state_dict().items()}
+    tsd = otimm.hf_to_timm(sd)
+    x = ovit.synthetic_images(3, seed=4)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    m = B200ViTForImageClassification.from_timm({"model": tsd})
+    assert m.config.tokens == 198 and m.config.head_rows == 2 and m.config.image_size == 224
+    _check(m(x.cuda()).logits, want)
+
+
 def test_full_size_config3_properties():
     """BASELINE config 3 at its full size (DeiT-Base, global batch 4096 as 4 chunks of 1024 -- the CTA-pair GEMMs at
     M = 201 728 rows): images are independent units, so the logits of any image must not depend on what it is batched

@@ -273,3 +273,25 @@ def test_two_tf_dialect_restatements_agree_and_einops_patterns_hold():
     img = torch.randn(2, 3, 32, 48)
     mine = img.reshape(2, 3, 2, 16, 3, 16).permute(0, 2, 4, 3, 5, 1).reshape(2, 6, 768)
     assert torch.equal(mine, rearrange(img, tf_vit_np.PATCHES, p1=16, p2=16))
+
+
+def test_distilled_timm_restatement_matches_hf_with_teacher():
+    """facebookresearch/deit ``DistilledVisionTransformer`` (dist_token, head_dist, eval output = mean of the two heads) restated in
+    oracle.timm_vit == HF ``DeiTForImageClassificationWithTeacher`` with eps 1e-6 on converted weights; the product's timm
+    adapter maps it back onto the two-head layout that ``normalise_keys`` folds into one classifier."""
+    from edgevisiontransformer_b200.dialects import timm_vit_to_canonical
+    from edgevisiontransformer_b200.modeling_vit import config_from_state_dict, normalise_keys
+    from oracle import timm_vit as otimm
+    hf = otimm.build_hf_distilled()
+    sd = {("vit." + k[5:] if k.startswith("deit.") else k): v.detach() for k, v in hf.state_dict().items()}
+    tsd = otimm.hf_to_timm(sd)
+    assert tsd["pos_embed"].shape == (1, 198, 192) and "head_dist.weight" in tsd
+    x = ovit.synthetic_images(2, seed=2)
+    with torch.no_grad():
+        want = hf(pixel_values=x).logits
+    assert (otimm.timm_vit_forward(tsd, x, num_heads=3) - want).abs().max() < 1e-5
+    csd, kw = timm_vit_to_canonical(tsd)
+    folded = normalise_keys(csd)
+    assert folded["classifier.weight"].shape == (1000, 384)
+    cfg = config_from_state_dict(folded, **kw)
+    assert cfg.head_rows == 2 and cfg.tokens == 198
